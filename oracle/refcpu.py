@@ -1,0 +1,109 @@
+"""TEST INFRASTRUCTURE — ctypes binding of oracle/_ref/libblitzar_ref_cpu.so.
+
+That library is the reference's own CPU MSM path (unmodified sources compiled by
+oracle/ref_build/Makefile) behind the thin `ref_*` driver in oracle/ref_build/ref_driver.cc.
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module; the product never does.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libblitzar_ref_cpu.so")
+
+CURVE_RISTRETTO255, CURVE_BLS_381, CURVE_BN_254, CURVE_GRUMPKIN = 0, 1, 2, 3
+# (projective, affine-as-passed-to-commit, normalised-output) byte sizes per curve
+SIZES = {0: (160, 160, 32), 1: (144, 104, 48), 2: (96, 72, 72), 3: (96, 72, 72)}
+
+
+class SequenceDescriptor(C.Structure):
+    """Layout of sxt_sequence_descriptor (cbindings/blitzar_api.h:115-131)."""
+    _fields_ = [("element_nbytes", C.c_uint8), ("n", C.c_uint64),
+                ("data", C.c_void_p), ("is_signed", C.c_int)]
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(LIB_PATH)
+        _lib.ref_sizeof.restype = C.c_uint
+    return _lib
+
+
+def make_descriptors(columns):
+    """columns: list of (np.ndarray uint8 [n, nbytes] C-contiguous, is_signed)."""
+    arr = (SequenceDescriptor * max(1, len(columns)))()
+    keep = []
+    for i, (data, is_signed) in enumerate(columns):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        keep.append(data)
+        arr[i].element_nbytes = data.shape[1]
+        arr[i].n = data.shape[0]
+        arr[i].data = data.ctypes.data if data.shape[0] else None
+        arr[i].is_signed = int(is_signed)
+    return arr, keep
+
+
+def ristretto_generators(n, offset=0):
+    out = np.zeros((n, 160), dtype=np.uint8)
+    if n:
+        lib().ref_ristretto255_get_generators(C.c_void_p(out.ctypes.data), C.c_uint64(n),
+                                              C.c_uint64(offset))
+    return out
+
+
+def random_elements(curve_id, n, first=0, affine=True):
+    psz, asz, _ = SIZES[curve_id]
+    p2 = np.zeros((n, psz), dtype=np.uint8)
+    af = np.zeros((n, asz), dtype=np.uint8)
+    lib().ref_random_elements(C.c_uint(curve_id), C.c_void_p(p2.ctypes.data),
+                              C.c_void_p(af.ctypes.data), C.c_uint64(n), C.c_uint64(first))
+    return (p2, af)
+
+
+def commit(curve_id, columns, generators=None, offset=0):
+    """Reference cpu-backend commitments. Returns uint8 [num_columns, out_size]."""
+    desc, keep = make_descriptors(columns)
+    out = np.zeros((len(columns), SIZES[curve_id][2]), dtype=np.uint8)
+    gp = C.c_void_p(generators.ctypes.data) if generators is not None else C.c_void_p(None)
+    L = lib()
+    if curve_id == 0:
+        L.ref_curve25519_commit(C.c_void_p(out.ctypes.data), C.c_uint32(len(columns)), desc, gp,
+                                C.c_uint64(offset))
+    else:
+        fn = {1: L.ref_bls12_381_g1_commit, 2: L.ref_bn254_g1_commit,
+              3: L.ref_grumpkin_commit}[curve_id]
+        fn(C.c_void_p(out.ctypes.data), C.c_uint32(len(columns)), desc, gp)
+    return out
+
+
+def normalize(curve_id, projective):
+    n = projective.shape[0]
+    out = np.zeros((n, SIZES[curve_id][2]), dtype=np.uint8)
+    lib().ref_normalize(C.c_uint(curve_id), C.c_void_p(out.ctypes.data),
+                        C.c_void_p(projective.ctypes.data), C.c_uint64(n))
+    return out
+
+
+def fixed_msm(curve_id, generators_p, num_outputs, n, scalars, element_num_bytes=0,
+              output_bit_table=None, output_lengths=None, window_width=4):
+    """Reference cpu fixed-base MSM (builds the partition table each call). Returns projective."""
+    res = np.zeros((num_outputs, SIZES[curve_id][0]), dtype=np.uint8)
+    mode = 0 if output_bit_table is None else (1 if output_lengths is None else 2)
+    bt = (C.c_uint * num_outputs)(*output_bit_table) if output_bit_table is not None else None
+    ol = (C.c_uint * num_outputs)(*output_lengths) if output_lengths is not None else None
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint8)
+    lib().ref_fixed_msm(C.c_uint(curve_id), C.c_void_p(res.ctypes.data),
+                        C.c_void_p(generators_p.ctypes.data), C.c_uint(generators_p.shape[0]),
+                        C.c_uint(window_width), C.c_int(mode), C.c_uint(element_num_bytes), bt, ol,
+                        C.c_uint(num_outputs), C.c_uint(n), C.c_void_p(scalars.ctypes.data))
+    return res
