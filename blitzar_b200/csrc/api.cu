@@ -1,0 +1,544 @@
+// C-ABI layer: the sxt_* drop-in entry points and the b200_* device-resident extension
+// (include/blitzar_b200.h). Host side is plain C++ over one CUDA stream; all arithmetic runs in
+// the kernels of msm.cuh. There is no CPU fallback: without a usable GPU sxt_init aborts, exactly
+// as the reference's gpu backend does (cbindings/backend.cc:50-64).
+//
+// Replaces: cbindings/{backend,pedersen,fixed_pedersen,get_generators,get_one_commit}.cc and the
+// gpu_backend methods they dispatch to (sxt/cbindings/backend/gpu_backend.cc:150-334).
+#include <cctype>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#define B200_EXTERN_CURVES
+#include "engine.cuh"
+
+using namespace b200;
+
+namespace {
+
+struct State {
+  bool initialized = false;
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  Ed25519::Gen* builtin = nullptr;  // g(0..num_builtin) device-resident
+  uint64_t num_builtin = 0;
+  MsmOptions opt;
+};
+State g_state;
+EngineCtx ctx() { return EngineCtx{g_state.stream, g_state.opt, g_state.builtin, g_state.num_builtin}; }
+std::mutex g_mutex;  // calls are serialised on the one library stream
+
+void ensure_device() {
+  if (g_state.stream)
+    return;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    die("no supported GPUs found (this library has no CPU fallback)", __FILE__, __LINE__);
+  if (g_state.device < 0) {
+    const char* env = std::getenv("BLITZAR_B200_DEVICE");
+    if (env)
+      g_state.device = std::atoi(env);
+    else
+      B200_CUDA(cudaGetDevice(&g_state.device));
+  }
+  B200_CUDA(cudaSetDevice(g_state.device));
+  B200_CUDA(cudaStreamCreateWithFlags(&g_state.stream, cudaStreamNonBlocking));
+  cudaMemPool_t pool;
+  B200_CUDA(cudaDeviceGetDefaultMemPool(&pool, g_state.device));
+  uint64_t threshold = UINT64_MAX;  // keep freed blocks cached in the pool between calls
+  B200_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+}
+
+void require_init(const char* fn) {
+  if (!g_state.initialized) {
+    std::fprintf(stderr, "blitzar_b200: backend uninitialized in `%s`\n", fn);
+    std::abort();
+  }
+  B200_CUDA(cudaSetDevice(g_state.device));
+}
+
+// host-pointer commitments: H2D, device MSM, D2H
+template <class C>
+void commit_host(void* commitments, uint32_t num, const sxt_sequence_descriptor* d,
+                 const void* generators, uint64_t offset_generators, const char* fn) {
+  if (num == 0)
+    return;
+  std::lock_guard<std::mutex> lock(g_mutex);
+  require_init(fn);
+  B200_REQUIRE(commitments != nullptr, "commitments == nullptr");
+  cudaStream_t s = g_state.stream;
+  uint64_t n = check_descriptors(d, num);
+  if (C::kCurveId != kRistretto255)
+    B200_REQUIRE(generators != nullptr, "generators == nullptr");
+  size_t total_scalar_bytes = 0;
+  for (uint32_t i = 0; i < num; ++i)
+    total_scalar_bytes += (size_t)d[i].n * d[i].element_nbytes + 32;
+  DevBuf<unsigned char> raw_gens(generators ? n * C::kAbiGenBytes : 1, s);
+  DevBuf<unsigned char> scal(total_scalar_bytes, s);
+  DevBuf<unsigned char> out(num * C::kAbiCommitBytes, s);
+  std::vector<sxt_sequence_descriptor> dd(d, d + num);
+  size_t off = 0;
+  for (uint32_t i = 0; i < num; ++i) {
+    size_t bytes = (size_t)d[i].n * d[i].element_nbytes;
+    copy_h2d(scal.p + off, d[i].data, bytes, s);
+    dd[i].data = scal.p + off;
+    off += (bytes + 31) & ~(size_t)31;
+  }
+  if (generators)
+    copy_h2d(raw_gens.p, generators, n * C::kAbiGenBytes, s);
+  CurveOps<C>::commit_device(ctx(), out.p, nullptr, num, dd.data(), generators ? raw_gens.p : nullptr,
+                   offset_generators);
+  copy_d2h(commitments, out.p, num * C::kAbiCommitBytes, s);
+  stream_sync(s);
+}
+
+template <class C> Handle* handle_new(const void* generators, unsigned n) {
+  cudaStream_t s = g_state.stream;
+  Handle* h = new Handle{C::kCurveId, n, nullptr};
+  B200_CUDA(cudaMalloc(&h->gens, (n ? n : 1) * sizeof(typename C::Gen)));
+  if (n) {
+    B200_REQUIRE(generators != nullptr, "generators == nullptr");
+    DevBuf<unsigned char> raw((size_t)n * C::kAbiProjBytes, s);
+    copy_h2d(raw.p, generators, (size_t)n * C::kAbiProjBytes, s);
+    CurveOps<C>::ingest_projective(ctx(), raw.p, h->gens, n);
+    stream_sync(s);
+  }
+  return h;
+}
+
+template <class C>
+void fixed_host(void* res, const Handle* h, int mode, unsigned element_num_bytes,
+                const unsigned* bit_table, const unsigned* lengths, unsigned num_outputs,
+                unsigned n, const uint8_t* scalars) {
+  if (num_outputs == 0)
+    return;
+  cudaStream_t s = g_state.stream;
+  uint64_t row_bits = 0;
+  unsigned rows = n;
+  for (unsigned j = 0; j < num_outputs; ++j) {
+    row_bits += mode == 0 ? 8ull * element_num_bytes : bit_table[j];
+    if (mode == 2) {
+      B200_REQUIRE(j == 0 || lengths[j] >= lengths[j - 1],
+                   "output lengths must be sorted in ascending order");
+      rows = j == 0 ? lengths[j] : (lengths[j] > rows ? lengths[j] : rows);
+    }
+  }
+  size_t bytes = (size_t)((row_bits + 7) / 8) * rows;
+  B200_REQUIRE(bytes == 0 || scalars != nullptr, "scalars == nullptr");
+  DevBuf<unsigned char> scal(bytes + 64, s);
+  DevBuf<unsigned char> out((size_t)num_outputs * C::kAbiProjBytes, s);
+  copy_h2d(scal.p, scalars, bytes, s);
+  CurveOps<C>::fixed_device(ctx(), out.p, nullptr, h, mode, element_num_bytes, bit_table, lengths, num_outputs,
+                  rows, scal.p);
+  copy_d2h(res, out.p, (size_t)num_outputs * C::kAbiProjBytes, s);
+  stream_sync(s);
+}
+
+template <class F> auto dispatch(unsigned curve_id, F f) {
+  switch (curve_id) {
+  case kRistretto255:
+    return f(Ed25519{});
+  case kBls12381:
+    return f(Bls12381G1{});
+  case kBn254:
+    return f(Bn254G1{});
+  case kGrumpkin:
+    return f(GrumpkinG{});
+  default:
+    die("unsupported curve id", __FILE__, __LINE__);
+  }
+}
+
+const uint32_t kHandleMagic = 0x44483242u;  // "B2HD"
+
+}  // namespace
+
+// =====================================================================================================
+// Part 1: sxt_*
+// =====================================================================================================
+extern "C" {
+
+int sxt_init(const struct sxt_config* config) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  if (config == nullptr)
+    die("config input to `sxt_init` is null", __FILE__, __LINE__);
+  if (g_state.initialized)
+    die("trying to reinitialize the backend in `sxt_init`", __FILE__, __LINE__);
+  int backend = config->backend;
+  if (const char* env = std::getenv("BLITZAR_BACKEND")) {
+    std::string v(env);
+    for (auto& ch : v)
+      ch = (char)std::tolower(ch);
+    if (v == "cpu")
+      backend = SXT_CPU_BACKEND;
+    else if (v == "gpu")
+      backend = SXT_GPU_BACKEND;
+    else
+      die("invalid BLITZAR_BACKEND value", __FILE__, __LINE__);
+  }
+  if (backend == SXT_CPU_BACKEND) {
+    std::fprintf(stderr, "blitzar_b200: this library provides only the gpu backend "
+                         "(SXT_GPU_BACKEND); link the reference libblitzar for the cpu backend\n");
+    return 2;
+  }
+  if (backend != SXT_GPU_BACKEND)
+    return 1;
+  ensure_device();
+  g_state.initialized = true;
+  uint64_t np = config->num_precomputed_generators;
+  if (np) {
+    B200_CUDA(cudaMalloc(&g_state.builtin, np * sizeof(Ed25519::Gen)));
+    launch_builtin_generators(ctx(), g_state.builtin, 0, np);
+    stream_sync(g_state.stream);
+    g_state.num_builtin = np;
+  }
+  return 0;
+}
+
+void sxt_curve25519_compute_pedersen_commitments(struct sxt_ristretto255_compressed* commitments,
+                                                 uint32_t num_sequences,
+                                                 const struct sxt_sequence_descriptor* descriptors,
+                                                 uint64_t offset_generators) {
+  commit_host<Ed25519>(commitments, num_sequences, descriptors, nullptr, offset_generators,
+                       "sxt_curve25519_compute_pedersen_commitments");
+}
+void sxt_curve25519_compute_pedersen_commitments_with_generators(
+    struct sxt_ristretto255_compressed* commitments, uint32_t num_sequences,
+    const struct sxt_sequence_descriptor* descriptors, const struct sxt_ristretto255* generators) {
+  // generators == nullptr falls back to the built-in generators at offset 0, as the reference does
+  // (cbindings/pedersen.cc:90-96)
+  commit_host<Ed25519>(commitments, num_sequences, descriptors, generators, 0,
+                       "sxt_curve25519_compute_pedersen_commitments_with_generators");
+}
+void sxt_bls12_381_g1_compute_pedersen_commitments_with_generators(
+    struct sxt_bls12_381_g1_compressed* commitments, uint32_t num_sequences,
+    const struct sxt_sequence_descriptor* descriptors, const struct sxt_bls12_381_g1* generators) {
+  commit_host<Bls12381G1>(commitments, num_sequences, descriptors, generators, 0,
+                          "sxt_bls12_381_g1_compute_pedersen_commitments_with_generators");
+}
+void sxt_bn254_g1_uncompressed_compute_pedersen_commitments_with_generators(
+    struct sxt_bn254_g1* commitments, uint32_t num_sequences,
+    const struct sxt_sequence_descriptor* descriptors, const struct sxt_bn254_g1* generators) {
+  commit_host<Bn254G1>(commitments, num_sequences, descriptors, generators, 0,
+                       "sxt_bn254_g1_uncompressed_compute_pedersen_commitments_with_generators");
+}
+void sxt_grumpkin_uncompressed_compute_pedersen_commitments_with_generators(
+    struct sxt_grumpkin* commitments, uint32_t num_sequences,
+    const struct sxt_sequence_descriptor* descriptors, const struct sxt_grumpkin* generators) {
+  commit_host<GrumpkinG>(commitments, num_sequences, descriptors, generators, 0,
+                         "sxt_grumpkin_uncompressed_compute_pedersen_commitments_with_generators");
+}
+
+int sxt_ristretto255_get_generators(struct sxt_ristretto255* generators, uint64_t num_generators,
+                                    uint64_t offset_generators) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  require_init("sxt_ristretto255_get_generators");
+  if (num_generators == 0)
+    return 0;
+  if (generators == nullptr)
+    return 1;
+  cudaStream_t s = g_state.stream;
+  DevBuf<Ed25519::Gen> gens(num_generators, s);
+  const Ed25519::Gen* src = gens.p;
+  if (offset_generators + num_generators <= g_state.num_builtin)
+    src = g_state.builtin + offset_generators;
+  else
+    launch_builtin_generators(ctx(), gens.p, offset_generators, num_generators);
+  DevBuf<unsigned char> out(num_generators * Ed25519::kAbiProjBytes, s);
+  CurveOps<Ed25519>::gens_to_projective(ctx(), src, out.p, num_generators);
+  copy_d2h(generators, out.p, num_generators * Ed25519::kAbiProjBytes, s);
+  stream_sync(s);
+  return 0;
+}
+
+int sxt_curve25519_get_one_commit(struct sxt_ristretto255* one_commit, uint64_t n) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  require_init("sxt_curve25519_get_one_commit");
+  B200_REQUIRE(one_commit != nullptr, "one_commit == nullptr");
+  B200_REQUIRE(n < (1ull << 31), "n too large");
+  cudaStream_t s = g_state.stream;
+  // sum of the first n built-in generators = MSM with all-one 1-byte scalars
+  DevBuf<unsigned char> ones(n + 32, s);
+  B200_CUDA(cudaMemsetAsync(ones.p, 1, n + 32, s));
+  sxt_sequence_descriptor d{1, n, ones.p, 0};
+  DevBuf<Ed25519::Point> pt(1, s);
+  DevBuf<unsigned char> out(Ed25519::kAbiProjBytes, s);
+  CurveOps<Ed25519>::commit_device(ctx(), nullptr, pt.p, 1, &d, nullptr, 0);
+  CurveOps<Ed25519>::store(ctx(), pt.p, out.p, 1, false);
+  copy_d2h(one_commit, out.p, Ed25519::kAbiProjBytes, s);
+  stream_sync(s);
+  return 0;
+}
+
+void sxt_curve25519_prove_inner_product(struct sxt_ristretto255_compressed*,
+                                        struct sxt_ristretto255_compressed*,
+                                        struct sxt_curve25519_scalar*, struct sxt_transcript*,
+                                        uint64_t, uint64_t, const struct sxt_curve25519_scalar*,
+                                        const struct sxt_curve25519_scalar*) {
+  die("sxt_curve25519_prove_inner_product is not provided by blitzar_b200 (MSM hot path only)",
+      __FILE__, __LINE__);
+}
+int sxt_curve25519_verify_inner_product(struct sxt_transcript*, uint64_t, uint64_t,
+                                        const struct sxt_curve25519_scalar*,
+                                        const struct sxt_curve25519_scalar*,
+                                        const struct sxt_ristretto255*,
+                                        const struct sxt_ristretto255_compressed*,
+                                        const struct sxt_ristretto255_compressed*,
+                                        const struct sxt_curve25519_scalar*) {
+  die("sxt_curve25519_verify_inner_product is not provided by blitzar_b200 (MSM hot path only)",
+      __FILE__, __LINE__);
+}
+void sxt_prove_sumcheck(void*, void*, unsigned, const struct sumcheck_descriptor*, void*, void*) {
+  die("sxt_prove_sumcheck is not provided by blitzar_b200 (MSM hot path only)", __FILE__,
+      __LINE__);
+}
+
+struct sxt_multiexp_handle* sxt_multiexp_handle_new(unsigned curve_id, const void* generators,
+                                                    unsigned n) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  require_init("sxt_multiexp_handle_new");
+  Handle* h = dispatch(curve_id, [&](auto c) { return handle_new<decltype(c)>(generators, n); });
+  return reinterpret_cast<sxt_multiexp_handle*>(h);
+}
+
+void sxt_multiexp_handle_free(struct sxt_multiexp_handle* handle) {
+  if (!handle)
+    return;
+  std::lock_guard<std::mutex> lock(g_mutex);
+  Handle* h = reinterpret_cast<Handle*>(handle);
+  B200_CUDA(cudaSetDevice(g_state.device));
+  B200_CUDA(cudaStreamSynchronize(g_state.stream));
+  B200_CUDA(cudaFree(h->gens));
+  delete h;
+}
+
+// File format (ours, versioned; the reference's [u32 window_width][partition table] format,
+// in_memory_partition_table_accessor.h:42-59, describes a different precomputation):
+//   u32 magic "B2HD", u32 version = 1, u32 curve_id, u32 n, then n projective ABI structs.
+void sxt_multiexp_handle_write_to_file(const struct sxt_multiexp_handle* handle,
+                                       const char* filename) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  require_init("sxt_multiexp_handle_write_to_file");
+  const Handle* h = reinterpret_cast<const Handle*>(handle);
+  B200_REQUIRE(h && filename, "null handle or filename");
+  cudaStream_t s = g_state.stream;
+  dispatch(h->curve_id, [&](auto c) {
+    typedef decltype(c) C;
+    size_t bytes = (size_t)h->n * C::kAbiProjBytes;
+    DevBuf<unsigned char> out(bytes + 16, s);
+    CurveOps<C>::gens_to_projective(ctx(), h->gens, out.p, h->n);
+    std::vector<unsigned char> host(bytes);
+    copy_d2h(host.data(), out.p, bytes, s);
+    stream_sync(s);
+    FILE* f = std::fopen(filename, "wb");
+    B200_REQUIRE(f != nullptr, "cannot open handle file for writing");
+    uint32_t hdr[4] = {kHandleMagic, 1u, h->curve_id, h->n};
+    B200_REQUIRE(std::fwrite(hdr, sizeof(hdr), 1, f) == 1, "short write");
+    B200_REQUIRE(bytes == 0 || std::fwrite(host.data(), bytes, 1, f) == 1, "short write");
+    std::fclose(f);
+    return 0;
+  });
+}
+
+struct sxt_multiexp_handle* sxt_multiexp_handle_new_from_file(unsigned curve_id,
+                                                              const char* filename) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  require_init("sxt_multiexp_handle_new_from_file");
+  B200_REQUIRE(filename != nullptr, "null filename");
+  FILE* f = std::fopen(filename, "rb");
+  B200_REQUIRE(f != nullptr, "cannot open handle file");
+  uint32_t hdr[4];
+  B200_REQUIRE(std::fread(hdr, sizeof(hdr), 1, f) == 1, "short handle file");
+  B200_REQUIRE(hdr[0] == kHandleMagic && hdr[1] == 1u, "not a blitzar_b200 handle file");
+  B200_REQUIRE(hdr[2] == curve_id, "handle file is for another curve");
+  Handle* h = dispatch(curve_id, [&](auto c) {
+    typedef decltype(c) C;
+    size_t bytes = (size_t)hdr[3] * C::kAbiProjBytes;
+    std::vector<unsigned char> host(bytes);
+    B200_REQUIRE(bytes == 0 || std::fread(host.data(), bytes, 1, f) == 1, "short handle file");
+    return handle_new<C>(host.data(), hdr[3]);
+  });
+  std::fclose(f);
+  return reinterpret_cast<sxt_multiexp_handle*>(h);
+}
+
+void sxt_fixed_multiexponentiation(void* res, const struct sxt_multiexp_handle* handle,
+                                   unsigned element_num_bytes, unsigned num_outputs, unsigned n,
+                                   const uint8_t* scalars) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  require_init("sxt_fixed_multiexponentiation");
+  const Handle* h = reinterpret_cast<const Handle*>(handle);
+  B200_REQUIRE(h != nullptr, "null handle");
+  dispatch(h->curve_id, [&](auto c) {
+    fixed_host<decltype(c)>(res, h, 0, element_num_bytes, nullptr, nullptr, num_outputs, n,
+                            scalars);
+    return 0;
+  });
+}
+void sxt_fixed_packed_multiexponentiation(void* res, const struct sxt_multiexp_handle* handle,
+                                          const unsigned* output_bit_table, unsigned num_outputs,
+                                          unsigned n, const uint8_t* scalars) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  require_init("sxt_fixed_packed_multiexponentiation");
+  const Handle* h = reinterpret_cast<const Handle*>(handle);
+  B200_REQUIRE(h != nullptr, "null handle");
+  dispatch(h->curve_id, [&](auto c) {
+    fixed_host<decltype(c)>(res, h, 1, 0, output_bit_table, nullptr, num_outputs, n, scalars);
+    return 0;
+  });
+}
+void sxt_fixed_vlen_multiexponentiation(void* res, const struct sxt_multiexp_handle* handle,
+                                        const unsigned* output_bit_table,
+                                        const unsigned* output_lengths, unsigned num_outputs,
+                                        const uint8_t* scalars) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  require_init("sxt_fixed_vlen_multiexponentiation");
+  const Handle* h = reinterpret_cast<const Handle*>(handle);
+  B200_REQUIRE(h != nullptr, "null handle");
+  dispatch(h->curve_id, [&](auto c) {
+    fixed_host<decltype(c)>(res, h, 2, 0, output_bit_table, output_lengths, num_outputs, 0,
+                            scalars);
+    return 0;
+  });
+}
+
+// =====================================================================================================
+// Part 2: b200_*
+// =====================================================================================================
+void b200_set_device(int device) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  B200_REQUIRE(g_state.stream == nullptr, "b200_set_device must precede sxt_init");
+  g_state.device = device;
+}
+unsigned long long b200_launch_count(void) { return LaunchCounter::value(); }
+unsigned b200_point_bytes(unsigned curve_id) {
+  return dispatch(curve_id, [](auto c) { return (unsigned)sizeof(typename decltype(c)::Point); });
+}
+void* b200_malloc(uint64_t bytes) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  require_init("b200_malloc");
+  void* p = nullptr;
+  B200_CUDA(cudaMalloc(&p, bytes ? bytes : 16));
+  return p;
+}
+void b200_free(void* p) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  if (p) {
+    B200_CUDA(cudaSetDevice(g_state.device));
+    B200_CUDA(cudaStreamSynchronize(g_state.stream));
+    B200_CUDA(cudaFree(p));
+  }
+}
+void b200_memcpy_h2d(void* d, const void* h, uint64_t bytes) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  require_init("b200_memcpy_h2d");
+  copy_h2d(d, h, bytes, g_state.stream);
+  stream_sync(g_state.stream);
+}
+void b200_memcpy_d2h(void* h, const void* d, uint64_t bytes) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  require_init("b200_memcpy_d2h");
+  copy_d2h(h, d, bytes, g_state.stream);
+  stream_sync(g_state.stream);
+}
+void b200_synchronize(void) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  require_init("b200_synchronize");
+  stream_sync(g_state.stream);
+}
+void* b200_event_create(void) {
+  require_init("b200_event_create");
+  cudaEvent_t e;
+  B200_CUDA(cudaEventCreate(&e));
+  return (void*)e;
+}
+void b200_event_record(void* e) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  B200_CUDA(cudaEventRecord((cudaEvent_t)e, g_state.stream));
+}
+float b200_event_elapsed_ms(void* a, void* b) {
+  float ms = 0;
+  B200_CUDA(cudaEventSynchronize((cudaEvent_t)b));
+  B200_CUDA(cudaEventElapsedTime(&ms, (cudaEvent_t)a, (cudaEvent_t)b));
+  return ms;
+}
+void b200_event_destroy(void* e) { B200_CUDA(cudaEventDestroy((cudaEvent_t)e)); }
+
+void b200_commit_device(unsigned curve_id, void* out_commitments, void* out_partials,
+                        uint32_t num_sequences, const struct sxt_sequence_descriptor* descriptors,
+                        const void* generators, uint64_t offset_generators) {
+  if (num_sequences == 0)
+    return;
+  std::lock_guard<std::mutex> lock(g_mutex);
+  require_init("b200_commit_device");
+  dispatch(curve_id, [&](auto c) {
+    CurveOps<decltype(c)>::commit_device(ctx(), out_commitments, out_partials, num_sequences,
+                                         descriptors, generators, offset_generators);
+    return 0;
+  });
+}
+void b200_combine_partials_device(unsigned curve_id, void* out_commitments, const void* partials,
+                                  uint32_t num_parts, uint32_t count) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  require_init("b200_combine_partials_device");
+  cudaStream_t s = g_state.stream;
+  dispatch(curve_id, [&](auto c) {
+    typedef decltype(c) C;
+    DevBuf<typename C::Point> sum(count, s);
+    CurveOps<C>::sum_parts(ctx(), partials, num_parts, count, sum.p);
+    CurveOps<C>::store(ctx(), sum.p, out_commitments, count, true);
+    return 0;
+  });
+}
+void b200_combine_partials_projective_device(unsigned curve_id, void* out_res,
+                                             const void* partials, uint32_t num_parts,
+                                             uint32_t count) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  require_init("b200_combine_partials_projective_device");
+  cudaStream_t s = g_state.stream;
+  dispatch(curve_id, [&](auto c) {
+    typedef decltype(c) C;
+    DevBuf<typename C::Point> sum(count, s);
+    CurveOps<C>::sum_parts(ctx(), partials, num_parts, count, sum.p);
+    CurveOps<C>::store(ctx(), sum.p, out_res, count, false);
+    return 0;
+  });
+}
+void b200_fixed_msm_device(void* out_res, void* out_partials,
+                           const struct sxt_multiexp_handle* handle, int mode,
+                           unsigned element_num_bytes, const unsigned* output_bit_table,
+                           const unsigned* output_lengths, unsigned num_outputs, unsigned n,
+                           const uint8_t* scalars) {
+  if (num_outputs == 0)
+    return;
+  std::lock_guard<std::mutex> lock(g_mutex);
+  require_init("b200_fixed_msm_device");
+  const Handle* h = reinterpret_cast<const Handle*>(handle);
+  B200_REQUIRE(h != nullptr, "null handle");
+  unsigned rows = n;
+  if (mode == 2) {
+    rows = 0;
+    for (unsigned j = 0; j < num_outputs; ++j)
+      rows = output_lengths[j] > rows ? output_lengths[j] : rows;
+  }
+  dispatch(h->curve_id, [&](auto c) {
+    CurveOps<decltype(c)>::fixed_device(ctx(), out_res, out_partials, h, mode,
+                                        element_num_bytes, output_bit_table, output_lengths,
+                                        num_outputs, rows, scalars);
+    return 0;
+  });
+}
+void b200_set_tuning(unsigned window_bits, unsigned chunk1, unsigned chunkn) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  g_state.opt.window_bits = window_bits;
+  g_state.opt.chunk1 = chunk1 ? chunk1 : 32;
+  g_state.opt.chunkn = chunkn ? chunkn : 8;
+}
+
+}  // extern "C"

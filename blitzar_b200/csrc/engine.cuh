@@ -1,0 +1,197 @@
+// Device-level glue between the C ABI and the MSM engine: descriptor validation, column grouping,
+// generator ingestion and result canonicalisation. Shared by api.cu (product) and the CPU-side
+// emulation harness under tests/emul (test infrastructure).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "../../include/blitzar_b200.h"
+#include "msm.cuh"
+
+namespace b200 {
+
+struct EngineCtx {
+  stream_t s;
+  MsmOptions opt;
+  const Ed25519::Gen* builtin;  // device-resident built-in generators g(0..num_builtin)
+  uint64_t num_builtin;
+};
+
+template <class T> struct DevBuf {
+  T* p = nullptr;
+  stream_t s;
+  DevBuf(size_t count, stream_t s_) : s(s_) { p = (T*)dev_alloc(count * sizeof(T), s); }
+  ~DevBuf() { dev_free(p, s); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+
+// ---- per-curve glue --------------------------------------------------------------------------------
+struct Handle {
+  unsigned curve_id;
+  unsigned n;
+  void* gens;  // device array of C::Gen
+};
+
+// validates like cbindings/pedersen.cc:44-68 and returns the longest column
+inline uint64_t check_descriptors(const sxt_sequence_descriptor* d, uint32_t num) {
+  B200_REQUIRE(d != nullptr, "descriptors == nullptr");
+  uint64_t longest = 0;
+  for (uint32_t i = 0; i < num; ++i) {
+    B200_REQUIRE(d[i].n == 0 || d[i].data != nullptr, "descriptor.n > 0 with data == nullptr");
+    B200_REQUIRE(d[i].element_nbytes != 0 && d[i].element_nbytes <= 32,
+                 "descriptor.element_nbytes must be in 1..32");
+    if (d[i].is_signed)
+      B200_REQUIRE(d[i].element_nbytes <= 16 &&
+                       (d[i].element_nbytes & (d[i].element_nbytes - 1)) == 0,
+                   "signed columns need a power-of-two element_nbytes <= 16");
+    B200_REQUIRE(d[i].n < (1ull << 31), "column too long");
+    longest = longest < d[i].n ? d[i].n : longest;
+  }
+  return longest;
+}
+
+// All kernel launches of one curve live behind CurveOps<C>, so each curve is instantiated in its
+// own translation unit (curve_*.cu) and api.cu only sees `extern template` declarations.
+template <class C> struct CurveOps {
+  typedef typename C::Gen Gen;
+  typedef typename C::Point Point;
+
+  // Columns are processed in groups so that (terms x windows) stays below 2^32 entries and the
+  // sort scratch stays within a few GB of HBM.
+  static void run_columns(const EngineCtx& ctx, const Gen* gens, std::vector<ColumnDesc>& cols,
+                          Point* out) {
+    const uint64_t kMaxEntries = 1ull << 30;
+    size_t b = 0;
+    while (b < cols.size()) {
+      size_t e = b;
+      uint64_t entries = 0;
+      while (e < cols.size()) {
+        uint64_t est = (uint64_t)cols[e].n * (cols[e].bit_width / 10 + 1);
+        if (e > b && entries + est > kMaxEntries)
+          break;
+        entries += est;
+        ++e;
+      }
+      std::vector<ColumnDesc> group(cols.begin() + b, cols.begin() + e);
+      msm_run<C>(ctx.s, gens, group, out + b, ctx.opt);
+      b = e;
+    }
+  }
+
+  // device-resident variable-base MSM; descriptors[i].data and generators_dev are device pointers
+  static void commit_device(const EngineCtx& ctx, void* out_commitments, void* out_partials,
+                            uint32_t num, const sxt_sequence_descriptor* d,
+                            const void* generators_dev, uint64_t offset_generators) {
+    stream_t s = ctx.s;
+    uint64_t n = check_descriptors(d, num);
+    DevBuf<Gen> gens(n ? n : 1, s);
+    const Gen* gens_ptr = gens.p;
+    if (n) {
+      if (generators_dev) {
+        launch(IngestBody<C, false>{(const unsigned char*)generators_dev, gens.p}, n, s);
+      } else {
+        if constexpr (C::kCurveId == kRistretto255) {
+          if (offset_generators + n <= ctx.num_builtin)
+            gens_ptr = ctx.builtin + offset_generators;
+          else
+            launch(BuiltinGeneratorBody{gens.p, offset_generators}, n, s);
+        } else {
+          die("generators == nullptr", __FILE__, __LINE__);
+        }
+      }
+    }
+    std::vector<ColumnDesc> cols(num);
+    for (uint32_t i = 0; i < num; ++i) {
+      cols[i].base = d[i].data;
+      cols[i].row_stride = d[i].element_nbytes;
+      cols[i].bit_offset = 0;
+      cols[i].bit_width = 8u * d[i].element_nbytes;
+      cols[i].n = (u32)d[i].n;
+      cols[i].is_signed = d[i].is_signed ? 1u : 0u;
+      cols[i].first_window = cols[i].num_windows = 0;
+    }
+    Point* pts = (Point*)out_partials;
+    DevBuf<Point> tmp(out_partials ? 1 : num, s);
+    if (!pts)
+      pts = tmp.p;
+    run_columns(ctx, gens_ptr, cols, pts);
+    if (out_commitments)
+      launch(StoreBody<C, true>{pts, (unsigned char*)out_commitments}, num, s);
+  }
+
+  // fixed-base MSM over a handle's device-resident generators (mode 0 fixed width, 1 packed, 2 vlen)
+  static void fixed_device(const EngineCtx& ctx, void* out_res, void* out_partials, const Handle* h,
+                           int mode, unsigned element_num_bytes, const unsigned* bit_table,
+                           const unsigned* lengths, unsigned num_outputs, unsigned n,
+                           const uint8_t* scalars_dev) {
+    stream_t s = ctx.s;
+    std::vector<ColumnDesc> cols(num_outputs);
+    uint64_t row_bits = 0;
+    if (mode == 0) {
+      B200_REQUIRE(element_num_bytes >= 1 && element_num_bytes <= 32, "element_num_bytes in 1..32");
+      row_bits = 8ull * element_num_bytes * num_outputs;
+    } else {
+      for (unsigned j = 0; j < num_outputs; ++j) {
+        B200_REQUIRE(bit_table[j] > 0 && bit_table[j] <= 256, "output bit width must be in 1..256");
+        row_bits += bit_table[j];
+      }
+    }
+    const uint64_t row_stride = (row_bits + 7) / 8;
+    uint64_t bit_off = 0;
+    for (unsigned j = 0; j < num_outputs; ++j) {
+      unsigned width = mode == 0 ? 8u * element_num_bytes : bit_table[j];
+      unsigned len = mode == 2 ? lengths[j] : n;
+      B200_REQUIRE(len <= h->n, "more scalars than generators in the handle");
+      cols[j].base = scalars_dev;
+      cols[j].row_stride = row_stride;
+      cols[j].bit_offset = (u32)bit_off;
+      cols[j].bit_width = width;
+      cols[j].n = len;
+      cols[j].is_signed = 0;
+      cols[j].first_window = cols[j].num_windows = 0;
+      bit_off += width;
+    }
+    Point* pts = (Point*)out_partials;
+    DevBuf<Point> tmp(out_partials ? 1 : (num_outputs ? num_outputs : 1), s);
+    if (!pts)
+      pts = tmp.p;
+    run_columns(ctx, (const Gen*)h->gens, cols, pts);
+    if (out_res)
+      launch(StoreBody<C, false>{pts, (unsigned char*)out_res}, num_outputs, s);
+  }
+
+  // projective ABI structs (device) -> device generator layout
+  static void ingest_projective(const EngineCtx& ctx, const void* raw_dev, void* gens, uint64_t n) {
+    launch(IngestBody<C, true>{(const unsigned char*)raw_dev, (Gen*)gens}, n, ctx.s);
+  }
+  static void gens_to_projective(const EngineCtx& ctx, const void* gens, void* out_dev,
+                                 uint64_t n) {
+    launch(GenToProjBody<C>{(const Gen*)gens, (unsigned char*)out_dev}, n, ctx.s);
+  }
+  // canonical commitments (commit = true) or projective ABI structs from accumulator points
+  static void store(const EngineCtx& ctx, const void* pts, void* out_dev, uint64_t count,
+                    bool commit) {
+    if (commit)
+      launch(StoreBody<C, true>{(const Point*)pts, (unsigned char*)out_dev}, count, ctx.s);
+    else
+      launch(StoreBody<C, false>{(const Point*)pts, (unsigned char*)out_dev}, count, ctx.s);
+  }
+  static void sum_parts(const EngineCtx& ctx, const void* parts, uint32_t nparts, uint32_t count,
+                        void* out_pts) {
+    launch(SumPartsBody<C>{(const Point*)parts, nparts, count, (Point*)out_pts}, count, ctx.s);
+  }
+};
+
+// built-in ristretto generators g(first .. first+n) into the device generator layout
+void launch_builtin_generators(const EngineCtx& ctx, Ed25519::Gen* gens, uint64_t first,
+                               uint64_t n);
+
+#ifdef B200_EXTERN_CURVES
+extern template struct CurveOps<Ed25519>;
+extern template struct CurveOps<Bls12381G1>;
+extern template struct CurveOps<Bn254G1>;
+extern template struct CurveOps<GrumpkinG>;
+#endif
+
+}  // namespace b200

@@ -1,0 +1,129 @@
+// Minimal launch / memory layer under the MSM engine.
+//
+// Replaces sxt/execution (coroutine futures + event-polling scheduler), sxt/memory (pmr device
+// resources) and sxt/algorithm/iteration/for_each.h for this path with plain CUDA streams and the
+// stream-ordered allocator: every kernel of the engine is an index-parallel body launched on one
+// stream; there is no host-side scheduling.
+//
+// With -DB200_EMULATE (tests/emul only) the same bodies run as serial host loops so the whole
+// pipeline can be exercised on a machine without a GPU. The product library is never built that
+// way and has no CPU fallback.
+#pragma once
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "field.cuh"
+
+#ifndef B200_EMULATE
+#include <cuda_runtime.h>
+#endif
+
+namespace b200 {
+
+[[noreturn]] inline void die(const char* what, const char* file, int line) {
+  std::fprintf(stderr, "blitzar_b200: fatal: %s (%s:%d)\n", what, file, line);
+  std::abort();
+}
+#define B200_REQUIRE(cond, msg)                                                                    \
+  do {                                                                                             \
+    if (!(cond))                                                                                   \
+      ::b200::die(msg, __FILE__, __LINE__);                                                        \
+  } while (0)
+
+#ifndef B200_EMULATE
+#define B200_CUDA(call)                                                                            \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      ::b200::die(cudaGetErrorString(e_), __FILE__, __LINE__);                                     \
+  } while (0)
+
+typedef cudaStream_t stream_t;
+
+template <class Body> __global__ void __launch_bounds__(Body::kBlock) k_run(Body body, u64 n) {
+  u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid < n)
+    body(tid);
+}
+
+struct LaunchCounter {
+  static unsigned long long& value() {
+    static unsigned long long v = 0;
+    return v;
+  }
+};
+
+template <class Body> inline void launch(const Body& body, u64 n, stream_t s) {
+  if (n == 0)
+    return;
+  u64 blocks = (n + Body::kBlock - 1) / Body::kBlock;
+  B200_REQUIRE(blocks < (1ull << 31), "grid too large");
+  k_run<Body><<<(unsigned)blocks, Body::kBlock, 0, s>>>(body, n);
+  B200_CUDA(cudaGetLastError());
+  ++LaunchCounter::value();
+}
+inline void* dev_alloc(size_t bytes, stream_t s) {
+  void* p = nullptr;
+  B200_CUDA(cudaMallocAsync(&p, bytes ? bytes : 16, s));
+  return p;
+}
+inline void dev_free(void* p, stream_t s) {
+  if (p)
+    B200_CUDA(cudaFreeAsync(p, s));
+}
+inline void dev_zero(void* p, size_t bytes, stream_t s) { B200_CUDA(cudaMemsetAsync(p, 0, bytes, s)); }
+inline void copy_h2d(void* d, const void* h, size_t bytes, stream_t s) {
+  if (bytes)
+    B200_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s));
+}
+inline void copy_d2h(void* h, const void* d, size_t bytes, stream_t s) {
+  if (bytes)
+    B200_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s));
+}
+inline void copy_d2d(void* d, const void* s_, size_t bytes, stream_t s) {
+  if (bytes)
+    B200_CUDA(cudaMemcpyAsync(d, s_, bytes, cudaMemcpyDeviceToDevice, s));
+}
+inline void stream_sync(stream_t s) { B200_CUDA(cudaStreamSynchronize(s)); }
+// the host half of a __host__ __device__ body is never executed in the product build
+template <class T> B200_HD T atomic_add(T* p, T v) {
+#ifdef __CUDA_ARCH__
+  return atomicAdd(p, v);
+#else
+  T old = *p;
+  *p = old + v;
+  return old;
+#endif
+}
+#define B200_ATOMIC_ADD(ptr, v) ::b200::atomic_add((ptr), (v))
+#else
+// ---- emulation: serial host loops ---------------------------------------------------------------
+typedef int stream_t;
+struct LaunchCounter {
+  static unsigned long long& value() {
+    static unsigned long long v = 0;
+    return v;
+  }
+};
+template <class Body> inline void launch(const Body& body, u64 n, stream_t) {
+  for (u64 t = 0; t < n; ++t)
+    body(t);
+  ++LaunchCounter::value();
+}
+inline void* dev_alloc(size_t bytes, stream_t) { return std::malloc(bytes ? bytes : 16); }
+inline void dev_free(void* p, stream_t) { std::free(p); }
+inline void dev_zero(void* p, size_t bytes, stream_t) { std::memset(p, 0, bytes); }
+inline void copy_h2d(void* d, const void* h, size_t bytes, stream_t) { std::memcpy(d, h, bytes); }
+inline void copy_d2h(void* h, const void* d, size_t bytes, stream_t) { std::memcpy(h, d, bytes); }
+inline void copy_d2d(void* d, const void* s_, size_t bytes, stream_t) { std::memcpy(d, s_, bytes); }
+inline void stream_sync(stream_t) {}
+template <class T> inline T emul_atomic_add(T* p, T v) {
+  T old = *p;
+  *p = old + v;
+  return old;
+}
+#define B200_ATOMIC_ADD(ptr, v) ::b200::emul_atomic_add((ptr), (v))
+#endif
+
+}  // namespace b200

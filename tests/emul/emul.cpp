@@ -1,0 +1,70 @@
+// TEST INFRASTRUCTURE — never linked into the product.
+//
+// Builds the product's kernel bodies (blitzar_b200/csrc/*.cuh) as SERIAL HOST LOOPS
+// (-DB200_EMULATE: launch() iterates the thread index, device memory is malloc) so that the whole
+// MSM pipeline — digit recoding, counting sort, chunked accumulation cascade, bucket reduction,
+// window combination, canonicalisation — can be checked against the oracle in a container without
+// a GPU. The product library (api.cu) has no such path and aborts without a GPU.
+#define __host__
+#define __device__
+#define __global__
+#define __forceinline__ inline __attribute__((always_inline))
+#include <cstdint>
+struct uint4 { uint32_t x, y, z, w; };
+#include "../../blitzar_b200/csrc/engine.cuh"
+
+using namespace b200;
+
+template <class F> static auto dispatch(unsigned curve_id, F f) {
+  switch (curve_id) {
+  case kRistretto255: return f(Ed25519{});
+  case kBls12381: return f(Bls12381G1{});
+  case kBn254: return f(Bn254G1{});
+  default: return f(GrumpkinG{});
+  }
+}
+
+static MsmOptions g_opt;
+
+extern "C" {
+void emul_set_tuning(unsigned window_bits, unsigned chunk1, unsigned chunkn) {
+  g_opt.window_bits = window_bits;
+  g_opt.chunk1 = chunk1 ? chunk1 : 32;
+  g_opt.chunkn = chunkn ? chunkn : 8;
+}
+// same contract as b200_commit_device, with host pointers standing in for device pointers
+void emul_commit(unsigned curve_id, void* out_commitments, uint32_t num,
+                 const sxt_sequence_descriptor* d, const void* generators, uint64_t offset) {
+  if (num == 0) return;
+  EngineCtx ctx{0, g_opt, nullptr, 0};
+  dispatch(curve_id, [&](auto c) {
+    CurveOps<decltype(c)>::commit_device(ctx, out_commitments, nullptr, num, d, generators, offset);
+    return 0;
+  });
+}
+void emul_get_generators(void* out160, uint64_t num, uint64_t offset) {
+  std::vector<Ed25519::Gen> g(num);
+  launch(BuiltinGeneratorBody{g.data(), offset}, num, 0);
+  launch(GenToProjBody<Ed25519>{g.data(), (unsigned char*)out160}, num, 0);
+}
+// handle_new + fixed MSM in one call (mode as in b200_fixed_msm_device)
+void emul_fixed(unsigned curve_id, void* res, const void* generators_proj, unsigned num_gens,
+                int mode, unsigned element_num_bytes, const unsigned* bit_table,
+                const unsigned* lengths, unsigned num_outputs, unsigned n, const uint8_t* scalars) {
+  EngineCtx ctx{0, g_opt, nullptr, 0};
+  dispatch(curve_id, [&](auto c) {
+    typedef decltype(c) C;
+    std::vector<typename C::Gen> gens(num_gens ? num_gens : 1);
+    launch(IngestBody<C, true>{(const unsigned char*)generators_proj, gens.data()}, num_gens, 0);
+    Handle h{curve_id, num_gens, gens.data()};
+    unsigned rows = n;
+    if (mode == 2) {
+      rows = 0;
+      for (unsigned j = 0; j < num_outputs; ++j) rows = lengths[j] > rows ? lengths[j] : rows;
+    }
+    CurveOps<C>::fixed_device(ctx, res, nullptr, &h, mode, element_num_bytes, bit_table, lengths,
+                    num_outputs, rows, scalars);
+    return 0;
+  });
+}
+}
