@@ -24,6 +24,91 @@ template <int N> struct alignas(16) Fe {
   u32 l[N];
 };
 
+
+// ------------------------------------------------------------------------------------------------
+// carry-flag primitives. Device: single PTX instructions chained through CC.CF (ptxas fuses a
+// mad.lo.cc / madc.hi.cc pair on one register pair into IMAD.WIDE.U32[.X]). Host (emulation and
+// the never-executed host half of __host__ __device__ bodies): the same semantics on an explicit
+// carry variable, so the identical limb schedules can be verified on a CPU.
+// ------------------------------------------------------------------------------------------------
+#ifdef __CUDA_ARCH__
+#define B200_CF_DECL
+B200_HD u32 add_cc(u32 a, u32 b) { u32 r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B200_HD u32 addc_cc(u32 a, u32 b) { u32 r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B200_HD u32 addc(u32 a, u32 b) { u32 r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B200_HD u32 sub_cc(u32 a, u32 b) { u32 r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B200_HD u32 subc_cc(u32 a, u32 b) { u32 r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B200_HD u32 subc(u32 a, u32 b) { u32 r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B200_HD u32 mad_lo_cc(u32 a, u32 b, u32 c) { u32 r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+B200_HD u32 madc_lo_cc(u32 a, u32 b, u32 c) { u32 r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+B200_HD u32 mad_hi_cc(u32 a, u32 b, u32 c) { u32 r; asm volatile("mad.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+B200_HD u32 madc_hi_cc(u32 a, u32 b, u32 c) { u32 r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+B200_HD u32 madc_hi(u32 a, u32 b, u32 c) { u32 r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+#else
+struct CarryFlag {
+  static u32& cf() {
+    static thread_local u32 v = 0;
+    return v;
+  }
+};
+inline u32 add_cc(u32 a, u32 b) { u64 t = (u64)a + b; CarryFlag::cf() = (u32)(t >> 32); return (u32)t; }
+inline u32 addc_cc(u32 a, u32 b) { u64 t = (u64)a + b + CarryFlag::cf(); CarryFlag::cf() = (u32)(t >> 32); return (u32)t; }
+inline u32 addc(u32 a, u32 b) { return a + b + CarryFlag::cf(); }
+inline u32 sub_cc(u32 a, u32 b) { u64 t = (u64)a - b; CarryFlag::cf() = (u32)(t >> 63); return (u32)t; }
+inline u32 subc_cc(u32 a, u32 b) { u64 t = (u64)a - b - CarryFlag::cf(); CarryFlag::cf() = (u32)(t >> 63); return (u32)t; }
+inline u32 subc(u32 a, u32 b) { return a - b - CarryFlag::cf(); }
+inline u32 mad_lo_cc(u32 a, u32 b, u32 c) { u64 t = (u64)(u32)(a * b) + c; CarryFlag::cf() = (u32)(t >> 32); return (u32)t; }
+inline u32 madc_lo_cc(u32 a, u32 b, u32 c) { u64 t = (u64)(u32)(a * b) + c + CarryFlag::cf(); CarryFlag::cf() = (u32)(t >> 32); return (u32)t; }
+inline u32 mad_hi_cc(u32 a, u32 b, u32 c) { u64 t = (((u64)a * b) >> 32) + c; CarryFlag::cf() = (u32)(t >> 32); return (u32)t; }
+inline u32 madc_hi_cc(u32 a, u32 b, u32 c) { u64 t = (((u64)a * b) >> 32) + c + CarryFlag::cf(); CarryFlag::cf() = (u32)(t >> 32); return (u32)t; }
+inline u32 madc_hi(u32 a, u32 b, u32 c) { return (u32)(((u64)a * b) >> 32) + c + CarryFlag::cf(); }
+#endif
+
+// acc[0..2*NP) += (x[0], x[2], x[4], ...)(NP limbs taken with stride 2) * y as NP non-overlapping
+// 64-bit products on the register pairs (acc[0],acc[1]), (acc[2],acc[3]), ... — one carry chain.
+// Leaves the carry-out in CC.CF. `first` = no incoming carry (starts the chain).
+template <int NP, class XS> B200_HD void chain_mad_pairs(u32* acc, XS x, u32 y) {
+  acc[0] = mad_lo_cc(x(0), y, acc[0]);
+  acc[1] = madc_hi_cc(x(0), y, acc[1]);
+#pragma unroll
+  for (int k = 1; k < NP; ++k) {
+    acc[2 * k] = madc_lo_cc(x(k), y, acc[2 * k]);
+    acc[2 * k + 1] = madc_hi_cc(x(k), y, acc[2 * k + 1]);
+  }
+}
+// same, but the chain starts by consuming the carry already in CC.CF
+template <int NP, class XS> B200_HD void chain_madc_pairs(u32* acc, XS x, u32 y) {
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    acc[2 * k] = madc_lo_cc(x(k), y, acc[2 * k]);
+    acc[2 * k + 1] = madc_hi_cc(x(k), y, acc[2 * k + 1]);
+  }
+}
+
+// 2N-limb product in even/odd form: E + (O << 32) = a * b, E[0..2N), O[0..2N-1) (O[k] sits at limb
+// position k+1). Every mad pair lands on an even-aligned register pair of E or O.
+template <int N> B200_HD void mul_wide_eo(u32* E, u32* O, const u32* a, const u32* b) {
+#pragma unroll
+  for (int i = 0; i < 2 * N; ++i) {
+    E[i] = 0;
+    O[i] = 0;
+  }
+#pragma unroll
+  for (int i = 0; i < N; i += 2) {
+    // row i (even): a_even*b[i] -> E[i..], a_odd*b[i] -> O[i..]
+    chain_mad_pairs<N / 2>(E + i, [a](int k) { return a[2 * k]; }, b[i]);
+    E[i + N] = addc(E[i + N], 0);
+    chain_mad_pairs<N / 2>(O + i, [a](int k) { return a[2 * k + 1]; }, b[i]);
+    O[i + N] = addc(O[i + N], 0);
+    // row i+1 (odd): a_even*b[i+1] sits at odd positions -> O[i..], a_odd*b[i+1] -> E[i+2..]
+    chain_mad_pairs<N / 2>(O + i, [a](int k) { return a[2 * k]; }, b[i + 1]);
+    O[i + N] = addc(O[i + N], 0);
+    chain_mad_pairs<N / 2>(E + i + 2, [a](int k) { return a[2 * k + 1]; }, b[i + 1]);
+    if (i + 2 + N < 2 * N)
+      E[i + 2 + N] = addc(E[i + 2 + N], 0);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // multi-limb add / sub
 // ------------------------------------------------------------------------------------------------
@@ -160,11 +245,39 @@ struct F25519 {
   }
   static B200_HD void dbl(E& r, const E& a) { add(r, a, a); }
 
-  // r = a*b. 16-limb product folded twice with 2^256 = 38.
-  static B200_HD void mul(E& r, const E& a, const E& b) {
+  // reference schedule (plain 64-bit C): r = a*b, 16-limb product folded twice with 2^256 = 38
+  static B200_HD void mul_ref(E& r, const E& a, const E& b) {
     u32 t[16];
     limbs_mul_wide<8>(t, a.l, b.l);
     fold(r, t);
+  }
+  // production schedule: 64 wide multiply-adds on even/odd register pairs (mul_wide_eo), one
+  // merge chain, then the 2^256 = 38 fold as a lo pass and a hi pass of mad.cc chains.
+  static B200_HD void mul(E& r, const E& a, const E& b) {
+    u32 Ev[16], Ov[16], R[16];
+    mul_wide_eo<8>(Ev, Ov, a.l, b.l);
+    R[0] = Ev[0];
+    R[1] = add_cc(Ev[1], Ov[0]);
+#pragma unroll
+    for (int k = 2; k < 16; ++k)
+      R[k] = addc_cc(Ev[k], Ov[k - 1]);
+    u32 t[8];
+    t[0] = mad_lo_cc(R[8], 38u, R[0]);
+#pragma unroll
+    for (int k = 1; k < 8; ++k)
+      t[k] = madc_lo_cc(R[8 + k], 38u, R[k]);
+    u32 c_lo = addc(0u, 0u);
+    t[1] = mad_hi_cc(R[8], 38u, t[1]);
+#pragma unroll
+    for (int k = 1; k < 7; ++k)
+      t[k + 1] = madc_hi_cc(R[8 + k], 38u, t[k + 1]);
+    u32 top = madc_hi(R[15], 38u, c_lo);  // < 2^7
+    r.l[0] = mad_lo_cc(top, 38u, t[0]);
+#pragma unroll
+    for (int k = 1; k < 8; ++k)
+      r.l[k] = addc_cc(t[k], 0u);
+    u32 c2 = addc(0u, 0u);
+    r.l[0] += 38u * c2;  // a wrap leaves a value < 2^12, so this cannot carry
   }
   static B200_HD void sqr(E& r, const E& a) { mul(r, a, a); }
 
@@ -391,8 +504,73 @@ template <class P> struct Mont {
       r.l[i] = pick_b ? b.l[i] : a.l[i];
   }
 
-  // CIOS Montgomery product: r = a*b/R mod p
+  // production schedule: CIOS Montgomery product on even/odd accumulators. Two limbs of b are
+  // consumed per frame (offsets 0 and 1) so that every multiply-add lands on an even-aligned
+  // register pair of Ev (limb positions k) or Ov (limb positions k+1); the frame then moves down
+  // by two limbs (register renaming). What the move cannot rename — Ov[1], which sits on the new
+  // position 0, and the carry bit out of the two zeroed limbs — is added to the new Ev by one
+  // N+1-instruction carry chain per frame.
   static B200_HD void mul(E& r, const E& a, const E& b) {
+    u32 Ev[N + 2], Ov[N + 2];
+#pragma unroll
+    for (int k = 0; k < N + 2; ++k) {
+      Ev[k] = 0;
+      Ov[k] = 0;
+    }
+    const u32* al = a.l;
+    auto a_even = [al](int k) { return al[2 * k]; };
+    auto a_odd = [al](int k) { return al[2 * k + 1]; };
+    auto p_even = [](int k) { return P::p(2 * k); };
+    auto p_odd = [](int k) { return P::p(2 * k + 1); };
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+      // ---- round A: b[i] at frame offset 0
+      chain_mad_pairs<N / 2>(Ev, a_even, b.l[i]);
+      Ev[N] = addc_cc(Ev[N], 0u);
+      Ev[N + 1] = addc(Ev[N + 1], 0u);
+      chain_mad_pairs<N / 2>(Ov, a_odd, b.l[i]);
+      Ov[N] = addc(Ov[N], 0u);
+      u32 m0 = Ev[0] * P::inv;
+      chain_mad_pairs<N / 2>(Ev, p_even, m0);
+      Ev[N] = addc_cc(Ev[N], 0u);
+      Ev[N + 1] = addc(Ev[N + 1], 0u);
+      chain_mad_pairs<N / 2>(Ov, p_odd, m0);
+      Ov[N] = addc(Ov[N], 0u);
+      // ---- round B: b[i+1] at frame offset 1
+      chain_mad_pairs<N / 2>(Ov, a_even, b.l[i + 1]);
+      Ov[N] = addc(Ov[N], 0u);
+      chain_mad_pairs<N / 2>(Ev + 2, a_odd, b.l[i + 1]);
+      u32 m1 = (Ev[1] + Ov[0]) * P::inv;
+      chain_mad_pairs<N / 2>(Ov, p_even, m1);
+      Ov[N] = addc(Ov[N], 0u);
+      chain_mad_pairs<N / 2>(Ev + 2, p_odd, m1);
+      // ---- move the frame down two limbs: Ev'[k] = Ev[k+2] + (k == 0 ? Ov[1] + carry : 0)
+      (void)add_cc(Ev[1], Ov[0]);  // the two dropped limbs sum to 0 mod 2^32; CF = their carry
+      Ev[0] = addc_cc(Ev[2], Ov[1]);
+#pragma unroll
+      for (int k = 1; k < N; ++k)
+        Ev[k] = addc_cc(Ev[k + 2], 0u);
+      Ev[N] = 0;
+      Ev[N + 1] = 0;
+#pragma unroll
+      for (int k = 0; k + 2 <= N; ++k)
+        Ov[k] = Ov[k + 2];
+      Ov[N - 1] = 0;
+      Ov[N] = 0;
+    }
+    E s, d, p = modulus();
+    s.l[0] = Ev[0];
+    s.l[1] = add_cc(Ev[1], Ov[0]);
+#pragma unroll
+    for (int k = 2; k < N; ++k)
+      s.l[k] = addc_cc(Ev[k], Ov[k - 1]);
+    u32 bw = limbs_sub<N>(d.l, s.l, p.l);
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      r.l[i] = bw ? s.l[i] : d.l[i];
+  }
+  // reference schedule (plain 64-bit C): CIOS Montgomery product r = a*b/R mod p
+  static B200_HD void mul_ref(E& r, const E& a, const E& b) {
     u32 t[N + 2];
 #pragma unroll
     for (int i = 0; i < N + 2; ++i)

@@ -1,0 +1,100 @@
+"""TEST INFRASTRUCTURE — ctypes binding of the C oracle port (oracle/msm_oracle.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module; the product never does. Same call shapes as oracle/refcpu.py so tests can swap them.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(_HERE, "msm_oracle.c")
+LIB_PATH = os.path.join(_HERE, "libmsm_oracle.so")
+SIZES = {0: (160, 160, 32), 1: (144, 104, 48), 2: (96, 72, 72), 3: (96, 72, 72)}
+
+
+class SequenceDescriptor(C.Structure):
+    _fields_ = [("element_nbytes", C.c_uint8), ("n", C.c_uint64), ("data", C.c_void_p),
+                ("is_signed", C.c_int)]
+
+
+_lib = None
+
+
+def build():
+    if not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(SRC):
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-w", SRC, "-o", LIB_PATH])
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+    return _lib
+
+
+def make_descriptors(columns):
+    arr = (SequenceDescriptor * max(1, len(columns)))()
+    keep = []
+    for i, (data, is_signed) in enumerate(columns):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        keep.append(data)
+        arr[i].element_nbytes = data.shape[1]
+        arr[i].n = data.shape[0]
+        arr[i].data = data.ctypes.data if data.shape[0] else None
+        arr[i].is_signed = int(is_signed)
+    return arr, keep
+
+
+def ristretto_generators(n, offset=0):
+    out = np.zeros((n, 160), dtype=np.uint8)
+    if n:
+        lib().oracle_ristretto255_get_generators(C.c_void_p(out.ctypes.data), C.c_uint64(n),
+                                                 C.c_uint64(offset))
+    return out
+
+
+def test_points(curve_id, n, seed=0):
+    """(projective ABI array, commitment-API affine array) of deterministic test points."""
+    psz, asz, _ = SIZES[curve_id]
+    p2 = np.zeros((n, psz), dtype=np.uint8)
+    af = np.zeros((n, asz), dtype=np.uint8)
+    lib().oracle_test_points(C.c_uint(curve_id), C.c_void_p(af.ctypes.data),
+                             C.c_void_p(p2.ctypes.data), C.c_uint64(n), C.c_uint64(seed))
+    return p2, af
+
+
+def commit(curve_id, columns, generators=None, offset=0):
+    desc, keep = make_descriptors(columns)
+    out = np.zeros((len(columns), SIZES[curve_id][2]), dtype=np.uint8)
+    gp = C.c_void_p(generators.ctypes.data) if generators is not None else C.c_void_p(None)
+    lib().oracle_commit(C.c_uint(curve_id), C.c_void_p(out.ctypes.data), C.c_uint32(len(columns)),
+                        desc, gp, C.c_uint64(offset))
+    return out
+
+
+def normalize(curve_id, projective):
+    n = projective.shape[0]
+    out = np.zeros((n, SIZES[curve_id][2]), dtype=np.uint8)
+    projective = np.ascontiguousarray(projective)
+    lib().oracle_normalize(C.c_uint(curve_id), C.c_void_p(out.ctypes.data),
+                           C.c_void_p(projective.ctypes.data), C.c_uint64(n))
+    return out
+
+
+def fixed_msm(curve_id, generators_p, num_outputs, n, scalars, element_num_bytes=0,
+              output_bit_table=None, output_lengths=None):
+    res = np.zeros((num_outputs, SIZES[curve_id][0]), dtype=np.uint8)
+    mode = 0 if output_bit_table is None else (1 if output_lengths is None else 2)
+    bt = (C.c_uint * num_outputs)(*output_bit_table) if output_bit_table is not None else None
+    ol = (C.c_uint * num_outputs)(*output_lengths) if output_lengths is not None else None
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint8)
+    generators_p = np.ascontiguousarray(generators_p)
+    lib().oracle_fixed_msm(C.c_uint(curve_id), C.c_void_p(res.ctypes.data),
+                           C.c_void_p(generators_p.ctypes.data), C.c_uint(generators_p.shape[0]),
+                           C.c_int(mode), C.c_uint(element_num_bytes), bt, ol,
+                           C.c_uint(num_outputs), C.c_uint(n), C.c_void_p(scalars.ctypes.data))
+    return res

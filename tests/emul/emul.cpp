@@ -68,3 +68,54 @@ void emul_fixed(unsigned curve_id, void* res, const void* generators_proj, unsig
   });
 }
 }
+
+// field-level cross-check: production multiply schedule vs the plain reference schedule
+template <class F> static int check_field(unsigned iters, unsigned seed) {
+  typename F::E a, b, r1, r2;
+  unsigned long long st = seed * 0x9E3779B97F4A7C15ull + 1;
+  auto next = [&st]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (u32)(st >> 16); };
+  int bad = 0;
+  for (unsigned it = 0; it < iters; ++it) {
+    for (int i = 0; i < F::N; ++i) { a.l[i] = next(); b.l[i] = next(); }
+    if (it % 7 == 0) for (int i = 0; i < F::N; ++i) a.l[i] = 0xffffffffu;
+    if (it % 11 == 0) for (int i = 0; i < F::N; ++i) b.l[i] = 0xffffffffu;
+    if (it % 13 == 0) for (int i = 0; i < F::N; ++i) b.l[i] = 0;
+    // Montgomery operands are residues < p: clear the top bits (p > 2^253 resp. 2^380)
+    a.l[F::N - 1] &= 0x0fffffffu;
+    b.l[F::N - 1] &= 0x0fffffffu;
+    if (it % 17 == 0) { a = F::modulus(); limbs_sub_small<F::N>(a.l, a.l, 1); }
+    if (it % 19 == 0) { b = F::modulus(); limbs_sub_small<F::N>(b.l, b.l, 1 + it % 3); }
+    F::mul(r1, a, b);
+    F::mul_ref(r2, a, b);
+    typename F::E c1 = r1, c2 = r2;
+    bool same = true;
+    for (int i = 0; i < F::N; ++i) same = same && (c1.l[i] == c2.l[i]);
+    if (!same) ++bad;
+  }
+  return bad;
+}
+extern "C" int emul_check_mul(unsigned field_id, unsigned iters, unsigned seed) {
+  switch (field_id) {
+  case 0: {
+    // F25519 results are only congruent mod p; compare canonical forms
+    int bad = 0;
+    F25519::E a, b, r1, r2, c1, c2;
+    unsigned long long st = seed * 0x9E3779B97F4A7C15ull + 1;
+    auto next = [&st]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (u32)(st >> 16); };
+    for (unsigned it = 0; it < iters; ++it) {
+      for (int i = 0; i < 8; ++i) { a.l[i] = next(); b.l[i] = next(); }
+      if (it % 7 == 0) for (int i = 0; i < 8; ++i) a.l[i] = 0xffffffffu;
+      if (it % 11 == 0) for (int i = 0; i < 8; ++i) b.l[i] = 0xffffffffu;
+      F25519::mul(r1, a, b);
+      F25519::mul_ref(r2, a, b);
+      F25519::canonical(c1, r1);
+      F25519::canonical(c2, r2);
+      for (int i = 0; i < 8; ++i) if (c1.l[i] != c2.l[i]) { ++bad; break; }
+    }
+    return bad;
+  }
+  case 1: return check_field<FBls>(iters, seed);
+  case 2: return check_field<FBn>(iters, seed);
+  default: return check_field<FGk>(iters, seed);
+  }
+}
