@@ -34,7 +34,8 @@ B200_SYMBOLS = [
     "b200_memcpy_h2d", "b200_memcpy_d2h", "b200_synchronize", "b200_event_create",
     "b200_event_record", "b200_event_elapsed_ms", "b200_event_destroy", "b200_commit_device",
     "b200_combine_partials_device", "b200_fixed_msm_device",
-    "b200_combine_partials_projective_device", "b200_set_tuning",
+    "b200_combine_partials_projective_device", "b200_set_tuning", "b200_profile_accumulate",
+    "b200_profile_read",
 ]
 
 
@@ -261,3 +262,28 @@ def synchronize():
 
 def launch_count():
     return int(lib().b200_launch_count())
+
+
+def profile_accumulate(enable):
+    lib().b200_profile_accumulate(C.c_int(1 if enable else 0))
+
+
+def profile_read():
+    """(total milliseconds, launches) of the level-1 accumulation kernel since the last read."""
+    ms, cnt = C.c_float(0), C.c_uint(0)
+    lib().b200_profile_read(C.byref(ms), C.byref(cnt))
+    return float(ms.value), int(cnt.value)
+
+
+def set_tuning(window_bits=0, chunk1=0, chunkn=0):
+    lib().b200_set_tuning(C.c_uint(window_bits), C.c_uint(chunk1), C.c_uint(chunkn))
+
+
+def combine_partials_device(curve_id, out_ptr, partials_ptr, num_parts, count):
+    lib().b200_combine_partials_device(C.c_uint(curve_id), C.c_void_p(out_ptr),
+                                       C.c_void_p(partials_ptr), C.c_uint32(num_parts),
+                                       C.c_uint32(count))
+
+
+def point_bytes(curve_id):
+    return int(lib().b200_point_bytes(C.c_uint(curve_id)))

@@ -534,6 +534,14 @@ void b200_fixed_msm_device(void* out_res, void* out_partials,
     return 0;
   });
 }
+void b200_profile_accumulate(int enable) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  KernelTimer::get().enabled = enable != 0;
+}
+void b200_profile_read(float* total_ms, unsigned* launches) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  KernelTimer::get().read(total_ms, launches);
+}
 void b200_set_tuning(unsigned window_bits, unsigned chunk1, unsigned chunkn) {
   std::lock_guard<std::mutex> lock(g_mutex);
   g_state.opt.window_bits = window_bits;

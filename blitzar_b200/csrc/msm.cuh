@@ -563,8 +563,10 @@ void msm_run(stream_t s, const typename C::Gen* gens, std::vector<ColumnDesc> co
 
   // accumulation cascade
   {
+    // a chunk of K entries leaves 2 pieces, so K must exceed 2 for the cascade to shrink
+    const u32 chunk1 = opt.chunk1 < 4 ? 4u : opt.chunk1, chunkn = opt.chunkn < 4 ? 4u : opt.chunkn;
     u64 m_max = max_entries;
-    u32 K = opt.chunk1;
+    u32 K = chunk1;
     const u32* lvl_keys = d_keys;
     const Point* lvl_pieces = nullptr;
     u32* m_ptr = d_m;
@@ -584,10 +586,12 @@ void msm_run(stream_t s, const typename C::Gen* gens, std::vector<ColumnDesc> co
         to_free.push_back(out_pieces);
       }
       if (first) {
+        KernelTimer::get().begin(s);
         launch(AccumulateBody<C, true>{lvl_keys, d_idx, gens, nullptr, m_ptr, K,
                                        final_level ? 1u : 0u, d_buckets, out_keys, out_pieces,
                                        out_m},
                T, s);
+        KernelTimer::get().end(s);
       } else {
         launch(AccumulateBody<C, false>{lvl_keys, nullptr, nullptr, lvl_pieces, m_ptr, K,
                                         final_level ? 1u : 0u, d_buckets, out_keys, out_pieces,
@@ -601,7 +605,7 @@ void msm_run(stream_t s, const typename C::Gen* gens, std::vector<ColumnDesc> co
       lvl_pieces = out_pieces;
       m_ptr = out_m;
       m_max = 2 * T;
-      K = opt.chunkn;
+      K = chunkn;
       ++level;
     }
     for (void* p : to_free)

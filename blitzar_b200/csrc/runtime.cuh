@@ -12,6 +12,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <utility>
+#include <vector>
 
 #include "field.cuh"
 
@@ -86,6 +88,46 @@ inline void copy_d2d(void* d, const void* s_, size_t bytes, stream_t s) {
     B200_CUDA(cudaMemcpyAsync(d, s_, bytes, cudaMemcpyDeviceToDevice, s));
 }
 inline void stream_sync(stream_t s) { B200_CUDA(cudaStreamSynchronize(s)); }
+
+// Optional per-launch timing of the dominant kernel (bucket accumulation, level 1) with CUDA events
+// on the launching stream — used by bench.py for the roofline line; off by default.
+struct KernelTimer {
+  bool enabled = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans;
+  static KernelTimer& get() {
+    static KernelTimer t;
+    return t;
+  }
+  void begin(stream_t s) {
+    if (!enabled)
+      return;
+    cudaEvent_t a, b;
+    B200_CUDA(cudaEventCreate(&a));
+    B200_CUDA(cudaEventCreate(&b));
+    B200_CUDA(cudaEventRecord(a, s));
+    spans.emplace_back(a, b);
+  }
+  void end(stream_t s) {
+    if (!enabled)
+      return;
+    B200_CUDA(cudaEventRecord(spans.back().second, s));
+  }
+  // total milliseconds and number of timed launches since the last read
+  void read(float* total_ms, unsigned* count) {
+    float tot = 0;
+    for (auto& sp : spans) {
+      float ms = 0;
+      B200_CUDA(cudaEventSynchronize(sp.second));
+      B200_CUDA(cudaEventElapsedTime(&ms, sp.first, sp.second));
+      tot += ms;
+      B200_CUDA(cudaEventDestroy(sp.first));
+      B200_CUDA(cudaEventDestroy(sp.second));
+    }
+    *total_ms = tot;
+    *count = (unsigned)spans.size();
+    spans.clear();
+  }
+};
 // the host half of a __host__ __device__ body is never executed in the product build
 template <class T> B200_HD T atomic_add(T* p, T v) {
 #ifdef __CUDA_ARCH__
@@ -118,6 +160,14 @@ inline void copy_h2d(void* d, const void* h, size_t bytes, stream_t) { std::memc
 inline void copy_d2h(void* h, const void* d, size_t bytes, stream_t) { std::memcpy(h, d, bytes); }
 inline void copy_d2d(void* d, const void* s_, size_t bytes, stream_t) { std::memcpy(d, s_, bytes); }
 inline void stream_sync(stream_t) {}
+struct KernelTimer {
+  static KernelTimer& get() {
+    static KernelTimer t;
+    return t;
+  }
+  void begin(stream_t) {}
+  void end(stream_t) {}
+};
 template <class T> inline T emul_atomic_add(T* p, T v) {
   T old = *p;
   *p = old + v;

@@ -194,6 +194,10 @@ void b200_fixed_msm_device(void* out_res, void* out_partials,
 void b200_combine_partials_projective_device(unsigned curve_id, void* out_res,
                                              const void* partials, uint32_t num_parts,
                                              uint32_t count);
+/* Per-launch CUDA-event timing of the dominant kernel (level-1 bucket accumulation) on the library
+ * stream: enable, run, then read the total milliseconds and launch count since the last read. */
+void b200_profile_accumulate(int enable);
+void b200_profile_read(float* total_ms, unsigned* launches);
 /* Engine tuning (0 keeps the default): window bits c, first-level and cascade chunk lengths. */
 void b200_set_tuning(unsigned window_bits, unsigned chunk1, unsigned chunkn);
 

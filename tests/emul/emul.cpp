@@ -119,3 +119,29 @@ extern "C" int emul_check_mul(unsigned field_id, unsigned iters, unsigned seed) 
   default: return check_field<FGk>(iters, seed);
   }
 }
+
+// multi-GPU host logic support: partial accumulator points and their combination
+extern "C" unsigned emul_point_bytes(unsigned curve_id) {
+  return dispatch(curve_id, [](auto c) { return (unsigned)sizeof(typename decltype(c)::Point); });
+}
+extern "C" void emul_commit_partial(unsigned curve_id, void* out_partials, uint32_t num,
+                                    const sxt_sequence_descriptor* d, const void* generators,
+                                    uint64_t offset) {
+  if (num == 0) return;
+  EngineCtx ctx{0, g_opt, nullptr, 0};
+  dispatch(curve_id, [&](auto c) {
+    CurveOps<decltype(c)>::commit_device(ctx, nullptr, out_partials, num, d, generators, offset);
+    return 0;
+  });
+}
+extern "C" void emul_combine_partials(unsigned curve_id, void* out_commitments, const void* partials,
+                                      uint32_t num_parts, uint32_t count) {
+  EngineCtx ctx{0, g_opt, nullptr, 0};
+  dispatch(curve_id, [&](auto c) {
+    typedef decltype(c) C;
+    std::vector<typename C::Point> sum(count);
+    CurveOps<C>::sum_parts(ctx, partials, num_parts, count, sum.data());
+    CurveOps<C>::store(ctx, sum.data(), out_commitments, count, true);
+    return 0;
+  });
+}

@@ -1,0 +1,117 @@
+"""TEST INFRASTRUCTURE — Python side of the CPU emulation harness (tests/emul/emul.cpp).
+
+Runs the product's kernel BODIES as serial host loops; used only by the `not gpu` tests to check
+the pipeline logic without a GPU. The product library never links or calls any of this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(_HERE))
+SRC = os.path.join(_HERE, "emul.cpp")
+LIB_PATH = os.path.join(_HERE, "libb200_emul.so")
+SIZES = {0: (160, 160, 32), 1: (144, 104, 48), 2: (96, 72, 72), 3: (96, 72, 72)}
+
+
+class SequenceDescriptor(C.Structure):
+    _fields_ = [("element_nbytes", C.c_uint8), ("n", C.c_uint64), ("data", C.c_void_p),
+                ("is_signed", C.c_int)]
+
+
+_lib = None
+
+
+def build():
+    csrc = os.path.join(ROOT, "blitzar_b200", "csrc")
+    deps = [SRC] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+    if not os.path.exists(LIB_PATH) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH)
+                                           for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-DB200_EMULATE", "-fPIC", "-shared",
+                               "-w", SRC, "-o", LIB_PATH])
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.emul_point_bytes.restype = C.c_uint
+    return _lib
+
+
+def _desc(columns):
+    arr = (SequenceDescriptor * max(1, len(columns)))()
+    keep = []
+    for i, (data, is_signed) in enumerate(columns):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        keep.append(data)
+        arr[i].element_nbytes = data.shape[1]
+        arr[i].n = data.shape[0]
+        arr[i].data = data.ctypes.data if data.shape[0] else None
+        arr[i].is_signed = int(is_signed)
+    return arr, keep
+
+
+def set_tuning(window_bits=0, chunk1=0, chunkn=0):
+    lib().emul_set_tuning(C.c_uint(window_bits), C.c_uint(chunk1), C.c_uint(chunkn))
+
+
+def commit(curve_id, columns, generators=None, offset=0):
+    desc, keep = _desc(columns)
+    out = np.zeros((len(columns), SIZES[curve_id][2]), dtype=np.uint8)
+    gp = C.c_void_p(generators.ctypes.data) if generators is not None else C.c_void_p(None)
+    lib().emul_commit(C.c_uint(curve_id), C.c_void_p(out.ctypes.data), C.c_uint32(len(columns)),
+                      desc, gp, C.c_uint64(offset))
+    return out
+
+
+def commit_partial(curve_id, columns, generators=None, offset=0):
+    desc, keep = _desc(columns)
+    pb = lib().emul_point_bytes(C.c_uint(curve_id))
+    out = np.zeros((len(columns), pb), dtype=np.uint8)
+    gp = C.c_void_p(generators.ctypes.data) if generators is not None else C.c_void_p(None)
+    lib().emul_commit_partial(C.c_uint(curve_id), C.c_void_p(out.ctypes.data),
+                              C.c_uint32(len(columns)), desc, gp, C.c_uint64(offset))
+    return out
+
+
+def combine_partials(curve_id, partials, num_parts, count):
+    out = np.zeros((count, SIZES[curve_id][2]), dtype=np.uint8)
+    partials = np.ascontiguousarray(partials)
+    lib().emul_combine_partials(C.c_uint(curve_id), C.c_void_p(out.ctypes.data),
+                                C.c_void_p(partials.ctypes.data), C.c_uint32(num_parts),
+                                C.c_uint32(count))
+    return out
+
+
+def point_bytes(curve_id):
+    return int(lib().emul_point_bytes(C.c_uint(curve_id)))
+
+
+def get_generators(n, offset=0):
+    out = np.zeros((n, 160), dtype=np.uint8)
+    lib().emul_get_generators(C.c_void_p(out.ctypes.data), C.c_uint64(n), C.c_uint64(offset))
+    return out
+
+
+def fixed_msm(curve_id, generators_p, num_outputs, n, scalars, element_num_bytes=0,
+              output_bit_table=None, output_lengths=None):
+    res = np.zeros((num_outputs, SIZES[curve_id][0]), dtype=np.uint8)
+    mode = 0 if output_bit_table is None else (1 if output_lengths is None else 2)
+    bt = (C.c_uint * num_outputs)(*output_bit_table) if output_bit_table is not None else None
+    ol = (C.c_uint * num_outputs)(*output_lengths) if output_lengths is not None else None
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint8)
+    scalars = np.concatenate([scalars.reshape(-1), np.zeros(64, dtype=np.uint8)])
+    generators_p = np.ascontiguousarray(generators_p)
+    lib().emul_fixed(C.c_uint(curve_id), C.c_void_p(res.ctypes.data),
+                     C.c_void_p(generators_p.ctypes.data), C.c_uint(generators_p.shape[0]),
+                     C.c_int(mode), C.c_uint(element_num_bytes), bt, ol, C.c_uint(num_outputs),
+                     C.c_uint(n), C.c_void_p(scalars.ctypes.data))
+    return res
+
+
+def check_mul(field_id, iters=2000, seed=1):
+    return int(lib().emul_check_mul(C.c_uint(field_id), C.c_uint(iters), C.c_uint(seed)))

@@ -1,0 +1,133 @@
+"""Pipeline logic on CPU: the product's kernel bodies run as serial host loops (tests/emul) and
+must agree bit-for-bit with the oracle. Mirrors the reference's shared conformance suite
+(sxt/multiexp/test/multiexponentiation.cc:42-451) and ABI tests (cbindings/pedersen.t.cc:243-612,
+cbindings/fixed_pedersen.t.cc:45-200)."""
+import numpy as np
+import pytest
+
+from tests import common
+
+
+def test_production_multiply_schedules_match_reference_schedules(emul):
+    # F25519, bls12-381, bn254, grumpkin: carry-chain even/odd schedule vs plain 64-bit schedule
+    for field_id in range(4):
+        assert emul.check_mul(field_id, 4000, seed=field_id + 1) == 0
+
+
+def test_golden_commitments(emul):
+    assert emul.commit(0, common.golden_columns()).tolist() == common.GOLDEN_COMMITMENTS
+
+
+def test_builtin_generators(emul, port):
+    g = emul.get_generators(9, 123)
+    assert np.array_equal(port.normalize(0, g), port.normalize(0, port.ristretto_generators(9, 123)))
+
+
+@pytest.mark.parametrize("curve", [0, 1, 2, 3])
+def test_edge_cases_all_curves(emul, port, curve):
+    gens, _ = common.generators_for(port, curve, 40)
+    cols = common.edge_case_columns()
+    assert common.same(curve, emul.commit(curve, cols, gens), port.commit(curve, cols, gens))
+
+
+@pytest.mark.parametrize("curve", [0, 1, 2, 3])
+def test_random_ragged_signed_columns(emul, port, curve):
+    rng = np.random.default_rng(100 + curve)
+    n = 700
+    gens, _ = common.generators_for(port, curve, n)
+    cols = common.random_columns(rng, n, [(0, 32, 0), (-13, 16, 1), (0, 8, 1), (-1, 5, 0),
+                                          (-699, 32, 0), (-700, 2, 0), (0, 1, 0)])
+    assert common.same(curve, emul.commit(curve, cols, gens), port.commit(curve, cols, gens))
+
+
+@pytest.mark.parametrize("window_bits", [2, 3, 5, 7, 8, 11, 13, 16])
+def test_every_window_width(emul, port, window_bits):
+    rng = np.random.default_rng(window_bits)
+    n = 300
+    gens, _ = common.generators_for(port, 0, n)
+    cols = common.random_columns(rng, n, [(0, 32, 0), (-3, 4, 1), (0, 7, 0)])
+    try:
+        emul.set_tuning(window_bits=window_bits)
+        got = emul.commit(0, cols, gens)
+    finally:
+        emul.set_tuning()
+    assert common.same(0, got, port.commit(0, cols, gens))
+
+
+@pytest.mark.parametrize("chunks", [(4, 4), (5, 4), (7, 5), (32, 8), (64, 16)])
+def test_cascade_chunk_shapes_and_skew(emul, port, chunks):
+    """Heavily skewed digits (all terms in one bucket) drive the multi-level cascade."""
+    rng = np.random.default_rng(5)
+    n = 900
+    gens, _ = common.generators_for(port, 0, n)
+    skew = np.full((n, 2), 0, dtype=np.uint8)
+    skew[:, 0] = 1
+    two = np.zeros((n, 4), dtype=np.uint8)
+    two[:, 0] = rng.integers(1, 3, n)
+    cols = [(skew, 0), (two, 0)] + common.random_columns(rng, n, [(0, 32, 0)])
+    try:
+        emul.set_tuning(chunk1=chunks[0], chunkn=chunks[1])
+        got = emul.commit(0, cols, gens)
+    finally:
+        emul.set_tuning()
+    assert common.same(0, got, port.commit(0, cols, gens))
+
+
+def test_homomorphism(emul, port):
+    """cbindings/pedersen.t.cc:287-316: commit(a) + commit(b) == commit(a + b)."""
+    rng = np.random.default_rng(9)
+    n = 64
+    a = rng.integers(0, 2**31, n, dtype=np.uint64)
+    b = rng.integers(0, 2**31, n, dtype=np.uint64)
+    cols = [(x.astype("<u8").view(np.uint8).reshape(n, 8), 0) for x in (a, b, a + b)]
+    gens, _ = common.generators_for(port, 0, n)
+    parts = emul.commit_partial(0, cols[:2], gens)
+    summed = emul.combine_partials(0, parts.reshape(2, -1), 2, 1)
+    assert np.array_equal(summed[0], emul.commit(0, cols[2:], gens)[0])
+
+
+@pytest.mark.parametrize("curve", [0, 1, 2, 3])
+def test_fixed_packed_vlen(emul, port, curve):
+    rng = np.random.default_rng(40 + curve)
+    m = 50
+    _, gens_p = common.generators_for(port, curve, m)
+    sc = rng.integers(0, 256, (m, 3 * 6), dtype=np.uint8)
+    a = emul.fixed_msm(curve, gens_p, 3, m, sc, element_num_bytes=6)
+    b = port.fixed_msm(curve, gens_p, 3, m, sc, element_num_bytes=6)
+    assert common.same(curve, port.normalize(curve, a), port.normalize(curve, b))
+    bt = [3, 1, 14, 9, 64, 5]
+    row = (sum(bt) + 7) // 8
+    psc = rng.integers(0, 256, (m, row), dtype=np.uint8)
+    a = emul.fixed_msm(curve, gens_p, len(bt), m, psc, output_bit_table=bt)
+    b = port.fixed_msm(curve, gens_p, len(bt), m, psc, output_bit_table=bt)
+    assert common.same(curve, port.normalize(curve, a), port.normalize(curve, b))
+    lens = [1, 2, 17, 17, 40, 50]
+    a = emul.fixed_msm(curve, gens_p, len(bt), m, psc, output_bit_table=bt, output_lengths=lens)
+    b = port.fixed_msm(curve, gens_p, len(bt), m, psc, output_bit_table=bt, output_lengths=lens)
+    assert common.same(curve, port.normalize(curve, a), port.normalize(curve, b))
+
+
+def test_reference_fixed_pedersen_vectors(emul, port):
+    """cbindings/fixed_pedersen.t.cc:121-135: packed {0b1010, 0b0101}, table {3,1}."""
+    g = port.ristretto_generators(2, 0)
+    res = emul.fixed_msm(0, g, 2, 2, np.array([0b1010, 0b0101], dtype=np.uint8),
+                         output_bit_table=[3, 1])
+    want = port.commit(0, [(np.array([[2], [5]], dtype=np.uint8), 0),
+                           (np.array([[1], [0]], dtype=np.uint8), 0)], g)
+    assert np.array_equal(port.normalize(0, res), want)
+
+
+def test_identity_generators_weierstrass(emul, port):
+    """Affine inputs flagged `infinity` are the group identity (element_affine::identity())."""
+    rng = np.random.default_rng(3)
+    for curve in (1, 2, 3):
+        gens, _ = common.generators_for(port, curve, 20)
+        gens = gens.copy()
+        stride = gens.shape[1]
+        flag = {1: 96, 2: 64, 3: 64}[curve]
+        for i in (0, 7, 19):
+            gens[i, :] = 0
+            gens[i, flag] = 1
+        cols = common.random_columns(rng, 20, [(0, 32, 0), (0, 2, 0)])
+        assert stride in (72, 104)
+        assert common.same(curve, emul.commit(curve, cols, gens), port.commit(curve, cols, gens))

@@ -1,0 +1,197 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (ctypes mirror in
+blitzar_b200/api.py), against the oracle on the same seeded inputs. Bit-exact: every output of
+this path is integer / byte data. Modelled on cbindings/pedersen.t.cc:243-612,
+cbindings/fixed_pedersen.t.cc:45-200, get_generators.t.cc, get_one_commit.t.cc and the shared
+conformance suite sxt/multiexp/test/multiexponentiation.cc:42-451."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import common
+
+pytestmark = pytest.mark.gpu
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_native_library_is_loaded(bb):
+    import blitzar_b200.api as api
+    maps = open("/proc/self/maps").read()
+    assert "libblitzar_b200.so" in maps
+    assert api.launch_count() > 0  # sxt_init precomputed generators with our kernel
+
+
+def test_reference_golden_commitments(bb):
+    out = bb.compute_pedersen_commitments(0, common.golden_columns())
+    assert out.tolist() == common.GOLDEN_COMMITMENTS
+
+
+def test_committed_reference_fixtures(bb, port):
+    for curve in range(4):
+        z = np.load(os.path.join(GOLDEN_DIR, f"commit_curve{curve}.npz"))
+        cols = [(z[f"col{j}"], int(z["signed"][j])) for j in range(len(z["signed"]))]
+        out = bb.compute_pedersen_commitments(curve, cols, z["generators"])
+        assert common.same(curve, out, z["commitments"]), curve
+        f = np.load(os.path.join(GOLDEN_DIR, f"fixed_curve{curve}.npz"))
+        h = bb.MultiexpHandle(curve, f["generators_p"])
+        res = h.fixed_multiexponentiation(int(f["element_num_bytes"]), int(f["num_outputs"]),
+                                          int(f["n"]), f["scalars"])
+        assert common.same(curve, port.normalize(curve, res), f["normalized"]), curve
+        res = h.fixed_packed_multiexponentiation(f["bit_table"].tolist(), int(f["n"]),
+                                                 f["packed_scalars"])
+        assert common.same(curve, port.normalize(curve, res), f["packed_normalized"]), curve
+        h.free()
+
+
+def test_num_sequences_zero_is_a_noop(bb):
+    out = bb.compute_pedersen_commitments(0, [])
+    assert out.shape[0] == 0
+
+
+def test_get_generators_and_one_commit(bb, port):
+    g = bb.get_generators(70, 60)  # straddles the 64 precomputed generators
+    assert np.array_equal(port.normalize(0, g), port.normalize(0, port.ristretto_generators(70, 60)))
+    for n in (0, 1, 5, 200):
+        one = bb.get_one_commit(n)
+        ones = np.ones((n, 1), dtype=np.uint8)
+        want = port.commit(0, [(ones, 0)], None, 0)
+        assert np.array_equal(port.normalize(0, one), want), n
+
+
+def test_generator_offset(bb, port):
+    rng = np.random.default_rng(4)
+    cols = common.random_columns(rng, 90, [(0, 8, 0), (-3, 32, 0)])
+    for offset in (0, 17, 1 << 33):
+        got = bb.compute_pedersen_commitments(0, cols, None, offset)
+        assert np.array_equal(got, port.commit(0, cols, None, offset)), offset
+
+
+@pytest.mark.parametrize("curve", [0, 1, 2, 3])
+def test_edge_cases(bb, port, curve):
+    gens, _ = common.generators_for(port, curve, 40)
+    cols = common.edge_case_columns()
+    assert common.same(curve, bb.compute_pedersen_commitments(curve, cols, gens),
+                       port.commit(curve, cols, gens))
+
+
+@pytest.mark.parametrize("curve", [0, 1, 2, 3])
+@pytest.mark.parametrize("n", [1, 31, 257, 4099, 20000])
+def test_random_sweep(bb, port, curve, n):
+    rng = np.random.default_rng(1000 * curve + n)
+    gens, _ = common.generators_for(port, curve, n)
+    cols = common.random_columns(rng, n, [(0, 32, 0), (-n // 3, 16, 1), (0, 8, 1), (0, 5, 0),
+                                          (-(n - 1), 32, 0), (-n, 2, 0), (0, 1, 0)])
+    assert common.same(curve, bb.compute_pedersen_commitments(curve, cols, gens),
+                       port.commit(curve, cols, gens))
+
+
+def test_skewed_digits_and_tuning(bb, port):
+    """All terms in one bucket; every window width; odd chunk shapes (cascade depth)."""
+    import ctypes as C
+    rng = np.random.default_rng(8)
+    n = 6000
+    gens, _ = common.generators_for(port, 0, n)
+    ones = np.zeros((n, 2), dtype=np.uint8)
+    ones[:, 0] = 1
+    cols = [(ones, 0)] + common.random_columns(rng, n, [(0, 32, 0), (0, 4, 1)])
+    want = port.commit(0, cols, gens)
+    try:
+        for c, k1, kn in [(2, 32, 8), (5, 7, 5), (8, 64, 4), (11, 16, 16), (13, 32, 8), (16, 32, 8)]:
+            bb.lib().b200_set_tuning(C.c_uint(c), C.c_uint(k1), C.c_uint(kn))
+            assert np.array_equal(bb.compute_pedersen_commitments(0, cols, gens), want), (c, k1, kn)
+    finally:
+        bb.lib().b200_set_tuning(C.c_uint(0), C.c_uint(0), C.c_uint(0))
+
+
+def test_homomorphism_through_partials(bb, port):
+    """cbindings/pedersen.t.cc:287-316 with the point addition done by the combine entry point."""
+    rng = np.random.default_rng(9)
+    n = 3000
+    a = rng.integers(0, 2**62, n, dtype=np.uint64)
+    b = rng.integers(0, 2**62, n, dtype=np.uint64)
+    cols = [(x.astype("<u8").view(np.uint8).reshape(n, 8), 0) for x in (a, b, a + b)]
+    gens, _ = common.generators_for(port, 0, n)
+    dg = bb.DeviceBuffer(host=gens)
+    ds = [bb.DeviceBuffer(host=c[0]) for c in cols]
+    pb = 128
+    parts = bb.DeviceBuffer(2 * pb)
+    bb.commit_device(0, [(n, 8, 0)] * 2, [ds[0].ptr, ds[1].ptr], dg.ptr, None, parts.ptr)
+    import ctypes as C
+    out = bb.DeviceBuffer(32)
+    bb.lib().b200_combine_partials_device(C.c_uint(0), C.c_void_p(out.ptr), C.c_void_p(parts.ptr),
+                                          C.c_uint32(2), C.c_uint32(1))
+    want = bb.compute_pedersen_commitments(0, cols[2:], gens)
+    assert np.array_equal(out.to_host()[:32], want[0])
+
+
+@pytest.mark.parametrize("curve", [0, 1, 2, 3])
+def test_fixed_packed_vlen_and_file_roundtrip(bb, port, curve, tmp_path):
+    rng = np.random.default_rng(40 + curve)
+    m = 300
+    _, gens_p = common.generators_for(port, curve, m)
+    h = bb.MultiexpHandle(curve, gens_p)
+    sc = rng.integers(0, 256, (m, 3 * 32), dtype=np.uint8)
+    a = h.fixed_multiexponentiation(32, 3, m, sc)
+    b = port.fixed_msm(curve, gens_p, 3, m, sc, element_num_bytes=32)
+    assert common.same(curve, port.normalize(curve, a), port.normalize(curve, b))
+    bt = [3, 1, 14, 9, 64, 5, 200]
+    row = (sum(bt) + 7) // 8
+    psc = rng.integers(0, 256, (m, row), dtype=np.uint8)
+    a = h.fixed_packed_multiexponentiation(bt, m, psc)
+    b = port.fixed_msm(curve, gens_p, len(bt), m, psc, output_bit_table=bt)
+    assert common.same(curve, port.normalize(curve, a), port.normalize(curve, b))
+    lens = [1, 2, 17, 17, 40, 50, 300]
+    a = h.fixed_vlen_multiexponentiation(bt, lens, psc)
+    b = port.fixed_msm(curve, gens_p, len(bt), m, psc, output_bit_table=bt, output_lengths=lens)
+    assert common.same(curve, port.normalize(curve, a), port.normalize(curve, b))
+    path = str(tmp_path / "handle.bin")
+    h.write_to_file(path)
+    h2 = bb.MultiexpHandle(curve, filename=path)
+    a2 = h2.fixed_packed_multiexponentiation(bt, m, psc)
+    assert common.same(curve, port.normalize(curve, a2), port.normalize(curve, a))
+    h.free()
+    h2.free()
+
+
+def test_reference_fixed_pedersen_vectors(bb, port):
+    g = port.ristretto_generators(2, 0)
+    h = bb.MultiexpHandle(0, g)
+    res = h.fixed_multiexponentiation(2, 1, 2, np.array([1, 0, 0, 2], dtype=np.uint8))
+    want = port.commit(0, [(np.array([[1, 0], [0, 2]], dtype=np.uint8), 0)], g)
+    assert np.array_equal(port.normalize(0, res), want)
+    res = h.fixed_packed_multiexponentiation([3, 1], 2, np.array([0b1010, 0b0101], dtype=np.uint8))
+    want = port.commit(0, [(np.array([[2], [5]], dtype=np.uint8), 0),
+                           (np.array([[1], [0]], dtype=np.uint8), 0)], g)
+    assert np.array_equal(port.normalize(0, res), want)
+    h.free()
+
+
+def test_full_size_properties_c2(bb, port):
+    """BASELINE config 2 size (ristretto, n = 2^20, 252-bit scalars): size-independent checks.
+    (1) linearity: MSM over [0,n) == sum of the MSMs over two halves (partials + combine);
+    (2) a 2^16 prefix with the remaining scalars zeroed equals the oracle on that prefix."""
+    import ctypes as C
+    n = 1 << 20
+    rng = np.random.default_rng(2)
+    s = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    s[:, 31] &= 0x0F
+    gens = bb.get_generators(n, 0)
+    full = bb.compute_pedersen_commitments(0, [(s, 0)], gens)
+    dg = bb.DeviceBuffer(host=gens)
+    ds = bb.DeviceBuffer(host=s)
+    parts = bb.DeviceBuffer(2 * 128)
+    half = n // 2
+    bb.commit_device(0, [(half, 32, 0)], [ds.ptr], dg.ptr, None, parts.ptr)
+    bb.commit_device(0, [(half, 32, 0)], [ds.ptr + half * 32], dg.ptr + half * 160, None,
+                     parts.ptr + 128)
+    out = bb.DeviceBuffer(32)
+    bb.lib().b200_combine_partials_device(C.c_uint(0), C.c_void_p(out.ptr), C.c_void_p(parts.ptr),
+                                          C.c_uint32(2), C.c_uint32(1))
+    assert np.array_equal(out.to_host()[:32], full[0])
+    m = 1 << 14
+    z = s.copy()
+    z[m:] = 0
+    got = bb.compute_pedersen_commitments(0, [(z, 0)], gens)
+    assert np.array_equal(got, port.commit(0, [(s[:m], 0)], gens[:m]))
+    for b_ in (dg, ds, parts, out):
+        b_.free()
