@@ -147,7 +147,7 @@ def test_fixed_packed_vlen_and_file_roundtrip(bb, port, curve, tmp_path):
     path = str(tmp_path / "handle.bin")
     h.write_to_file(path)
     h2 = bb.MultiexpHandle(curve, filename=path)
-    a2 = h2.fixed_packed_multiexponentiation(bt, m, psc)
+    a2 = h2.fixed_vlen_multiexponentiation(bt, lens, psc)
     assert common.same(curve, port.normalize(curve, a2), port.normalize(curve, a))
     h.free()
     h2.free()
