@@ -35,7 +35,7 @@ B200_SYMBOLS = [
     "b200_event_record", "b200_event_elapsed_ms", "b200_event_destroy", "b200_commit_device",
     "b200_combine_partials_device", "b200_fixed_msm_device",
     "b200_combine_partials_projective_device", "b200_set_tuning", "b200_profile_accumulate",
-    "b200_profile_read",
+    "b200_profile_read", "b200_set_reduce_groups",
 ]
 
 
@@ -287,3 +287,7 @@ def combine_partials_device(curve_id, out_ptr, partials_ptr, num_parts, count):
 
 def point_bytes(curve_id):
     return int(lib().b200_point_bytes(C.c_uint(curve_id)))
+
+
+def set_reduce_groups(g1=0, gn=0):
+    lib().b200_set_reduce_groups(C.c_uint(g1), C.c_uint(gn))

@@ -534,6 +534,19 @@ void b200_fixed_msm_device(void* out_res, void* out_partials,
     return 0;
   });
 }
+void b200_set_reduce_groups(unsigned g1, unsigned gn) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  auto pow2 = [](unsigned v, unsigned dflt) {
+    if (v < 2)
+      return dflt;
+    unsigned p = 2;
+    while (p * 2 <= v)
+      p *= 2;
+    return p;
+  };
+  g_state.opt.reduce_g1 = pow2(g1, 8u);
+  g_state.opt.reduce_gn = pow2(gn, 8u);
+}
 void b200_profile_accumulate(int enable) {
   std::lock_guard<std::mutex> lock(g_mutex);
   KernelTimer::get().enabled = enable != 0;

@@ -33,7 +33,11 @@ struct Ed25519 {
   struct Point {
     fe X, Y, Z, T;
   };
-  typedef Point Gen;
+  // generator as kept in HBM: "cached" form (Y+X, Y-X, 2Z, 2dT) so that a bucket add costs 8
+  // field multiplications (the 2d*T product is paid once per generator at ingestion)
+  struct Gen {
+    fe YpX, YmX, Z2, T2d;
+  };
 
   static B200_HD Point identity() {
     Point p;
@@ -71,20 +75,46 @@ struct Ed25519 {
     F::mul(r.T, E, H);
     F::mul(r.Z, Fv, G);
   }
-  static B200_HD void add_gen(Point& r, const Point& a, const Gen& g, bool negate) {
-    if (negate) {
-      Gen n;
-      neg(n, g);
-      add(r, a, n);
-    } else {
-      add(r, a, g);
-    }
+  static B200_HD void point_to_gen(Gen& g, const Point& p) {
+    F::add(g.YpX, p.Y, p.X);
+    F::sub(g.YmX, p.Y, p.X);
+    F::dbl(g.Z2, p.Z);
+    F::mul(g.T2d, p.T, F::constant([](int i) { return F25_D2(i); }));
   }
+  // (2X : 2Y : 2Z : 2T) — the same point; one multiplication by the constant 1/d
   static B200_HD void gen_to_point(Point& r, const Gen& g, bool negate) {
-    if (negate)
-      neg(r, g);
-    else
-      r = g;
+    fe x2, t2, nx, nt;
+    F::sub(x2, g.YpX, g.YmX);
+    F::add(r.Y, g.YpX, g.YmX);
+    r.Z = g.Z2;
+    F::mul(t2, g.T2d, F::constant([](int i) { return F25_INVD(i); }));
+    F::neg(nx, x2);
+    F::neg(nt, t2);
+    F::select(r.X, x2, nx, negate);
+    F::select(r.T, t2, nt, negate);
+  }
+  // r = a +/- g in 8 multiplications; branch-free in `negate` (-g swaps Y+X / Y-X and negates 2dT)
+  // so the lanes of a warp add generators of either sign in one pass
+  static B200_HD void add_gen(Point& r, const Point& a, const Gen& g, bool negate) {
+    fe A, B, C, D, E, Fv, G, H, t0, t1, qp, qm, qt, nt;
+    F::select(qp, g.YpX, g.YmX, negate);
+    F::select(qm, g.YmX, g.YpX, negate);
+    F::neg(nt, g.T2d);
+    F::select(qt, g.T2d, nt, negate);
+    F::sub(t0, a.Y, a.X);
+    F::mul(A, t0, qm);
+    F::add(t1, a.Y, a.X);
+    F::mul(B, t1, qp);
+    F::mul(C, a.T, qt);
+    F::mul(D, a.Z, g.Z2);
+    F::sub(E, B, A);
+    F::sub(Fv, D, C);
+    F::add(G, D, C);
+    F::add(H, B, A);
+    F::mul(r.X, E, Fv);
+    F::mul(r.Y, G, H);
+    F::mul(r.T, E, H);
+    F::mul(r.Z, Fv, G);
   }
   static B200_HD void dbl(Point& r, const Point& a) {
     fe A, B, C, E, Fv, G, H, t0;
@@ -107,10 +137,12 @@ struct Ed25519 {
   // sxt_ristretto255 { u64 X[5], Y[5], Z[5], T[5] }
   static B200_HD void load_gen_abi(Gen& g, const void* src) {
     const u64* s = (const u64*)src;
-    F::from_radix51(g.X, s);
-    F::from_radix51(g.Y, s + 5);
-    F::from_radix51(g.Z, s + 10);
-    F::from_radix51(g.T, s + 15);
+    Point p;
+    F::from_radix51(p.X, s);
+    F::from_radix51(p.Y, s + 5);
+    F::from_radix51(p.Z, s + 10);
+    F::from_radix51(p.T, s + 15);
+    point_to_gen(g, p);
   }
   static B200_HD void load_proj_abi(Gen& g, const void* src) { load_gen_abi(g, src); }
   static B200_HD void store_proj_abi(void* dst, const Point& p) {
@@ -334,9 +366,9 @@ template <class FieldT, class CP> struct Weierstrass {
       r = p;
       return;
     }
-    fe qy = g.y;
-    if (negate)
-      F::neg(qy, g.y);
+    fe qy, ny;
+    F::neg(ny, g.y);
+    F::select(qy, g.y, ny, negate);
     fe t0, t1, t2, t3, t4, x3, y3, z3;
     F::mul(t0, p.X, g.x);
     F::mul(t1, p.Y, qy);
@@ -373,10 +405,10 @@ template <class FieldT, class CP> struct Weierstrass {
       r = identity();
       return;
     }
+    fe ny;
+    F::neg(ny, g.y);
     r.X = g.x;
-    r.Y = g.y;
-    if (negate)
-      F::neg(r.Y, g.y);
+    F::select(r.Y, g.y, ny, negate);
     r.Z = F::one();
   }
   // RCB16 Algorithm 9 (a = 0)

@@ -350,8 +350,50 @@ struct F25519 {
   struct ExpP58 {  // (p-5)/8 = 2^252 - 3
     B200_HD u32 operator()(int i) const { return i == 0 ? 0xfffffffdu : (i == 7 ? 0x0fffffffu : 0xffffffffu); }
   };
-  static B200_HD void invert(E& r, const E& a) { pow(r, a, ExpPm2{}); }
-  static B200_HD void pow22523(E& r, const E& a) { pow(r, a, ExpP58{}); }
+  static B200_HD void sqr_n(E& r, const E& a, int n) {
+    r = a;
+    for (int i = 0; i < n; ++i)
+      sqr(r, r);
+  }
+  // a^(2^250 - 1), the shared prefix of the two fixed exponents (standard 2^k-1 ladder)
+  static B200_HD void pow_2_250_m1(E& r, E& a11, const E& a) {
+    E t0, t1, t2, t3;
+    sqr(t0, a);             // 2
+    sqr_n(t1, t0, 2);       // 8
+    mul(t1, a, t1);         // 9
+    mul(t0, t0, t1);        // 11
+    a11 = t0;
+    sqr(t2, t0);            // 22
+    mul(t1, t1, t2);        // 31 = 2^5 - 1
+    sqr_n(t2, t1, 5);
+    mul(t1, t2, t1);        // 2^10 - 1
+    sqr_n(t2, t1, 10);
+    mul(t2, t2, t1);        // 2^20 - 1
+    sqr_n(t3, t2, 20);
+    mul(t2, t3, t2);        // 2^40 - 1
+    sqr_n(t2, t2, 10);
+    mul(t1, t2, t1);        // 2^50 - 1
+    sqr_n(t2, t1, 50);
+    mul(t2, t2, t1);        // 2^100 - 1
+    sqr_n(t3, t2, 100);
+    mul(t2, t3, t2);        // 2^200 - 1
+    sqr_n(t2, t2, 50);
+    mul(r, t2, t1);         // 2^250 - 1
+  }
+  // a^(p-2) = a^(2^255 - 21): (2^250-1) << 5 | 11
+  static B200_HD void invert(E& r, const E& a) {
+    E t, a11;
+    pow_2_250_m1(t, a11, a);
+    sqr_n(t, t, 5);
+    mul(r, t, a11);
+  }
+  // a^((p-5)/8) = a^(2^252 - 3): (2^250-1) << 2 | 1
+  static B200_HD void pow22523(E& r, const E& a) {
+    E t, a11;
+    pow_2_250_m1(t, a11, a);
+    sqr_n(t, t, 2);
+    mul(r, t, a);
+  }
 
   // radix-2^51 limbs (sxt_ristretto255 / c21t::element_p3 field layout; limbs may be unreduced)
   static B200_HD void from_radix51(E& r, const u64* h) {

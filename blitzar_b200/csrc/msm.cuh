@@ -437,7 +437,7 @@ struct BuiltinGeneratorBody {
   B200_HD void operator()(u64 i) const {
     Ed25519::Point g;
     Ed25519::builtin_generator(g, first + i);
-    gens[i] = g;
+    Ed25519::point_to_gen(gens[i], g);
   }
 };
 // result canonicalisation
@@ -495,6 +495,8 @@ struct MsmOptions {
   u32 window_bits = 0;  // 0 = choose from n
   u32 chunk1 = 32;      // chunk length of the first accumulation level
   u32 chunkn = 8;       // chunk length of the cascade levels
+  u32 reduce_g1 = 8;    // bucket-reduction group size, first level (power of two)
+  u32 reduce_gn = 8;    // bucket-reduction group size, later levels (power of two)
 };
 
 // Computes out[j] = sum_i scalar(j,i) * G_i for every column j. `cols` are host descriptors whose
@@ -628,7 +630,7 @@ void msm_run(stream_t s, const typename C::Gen* gens, std::vector<ColumnDesc> co
     }
     bool first = true;
     while (m > 1) {
-      u32 g = first ? std::min<u32>(32u, m) : std::min<u32>(8u, m);
+      u32 g = first ? std::min<u32>(opt.reduce_g1, m) : std::min<u32>(opt.reduce_gn, m);
       u32 log2g = 0;
       while ((1u << log2g) < g)
         ++log2g;

@@ -200,6 +200,8 @@ void b200_profile_accumulate(int enable);
 void b200_profile_read(float* total_ms, unsigned* launches);
 /* Engine tuning (0 keeps the default): window bits c, first-level and cascade chunk lengths. */
 void b200_set_tuning(unsigned window_bits, unsigned chunk1, unsigned chunkn);
+/* Bucket-reduction group sizes (powers of two; 0 keeps the default): first level, later levels. */
+void b200_set_reduce_groups(unsigned g1, unsigned gn);
 
 #ifdef __cplusplus
 }
