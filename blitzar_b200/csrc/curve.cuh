@@ -18,6 +18,88 @@ namespace b200 {
 
 enum CurveId : unsigned { kRistretto255 = 0, kBls12381 = 1, kBn254 = 2, kGrumpkin = 3 };
 
+// ---- execution policies for the independent field multiplications inside a point operation -------
+// SeqExec : one thread computes every product (throughput-bound kernels).
+// QuadExec: four adjacent lanes hold identical operands; each lane computes one product of a batch
+//           and the results are broadcast with warp shuffles, so a point operation costs 2-4
+//           multiplication latencies instead of 8-12 (latency-bound tail kernels). All four lanes
+//           execute the same instruction stream on lane-selected operands (no divergence). On the
+//           host (emulation) both policies compute every product.
+struct SeqExec {
+  static constexpr int kLanes = 1;
+  template <class F>
+  static B200_HD void mul4(typename F::E& o0, typename F::E& o1, typename F::E& o2,
+                           typename F::E& o3, const typename F::E& a0, const typename F::E& b0,
+                           const typename F::E& a1, const typename F::E& b1,
+                           const typename F::E& a2, const typename F::E& b2,
+                           const typename F::E& a3, const typename F::E& b3) {
+    F::mul(o0, a0, b0);
+    F::mul(o1, a1, b1);
+    F::mul(o2, a2, b2);
+    F::mul(o3, a3, b3);
+  }
+  template <class F>
+  static B200_HD void mul2(typename F::E& o0, typename F::E& o1, const typename F::E& a0,
+                           const typename F::E& b0, const typename F::E& a1,
+                           const typename F::E& b1) {
+    F::mul(o0, a0, b0);
+    F::mul(o1, a1, b1);
+  }
+};
+struct QuadExec {
+  static constexpr int kLanes = 4;
+  template <class F>
+  static B200_HD void mul4(typename F::E& o0, typename F::E& o1, typename F::E& o2,
+                           typename F::E& o3, const typename F::E& a0, const typename F::E& b0,
+                           const typename F::E& a1, const typename F::E& b1,
+                           const typename F::E& a2, const typename F::E& b2,
+                           const typename F::E& a3, const typename F::E& b3) {
+#ifdef __CUDA_ARCH__
+    const unsigned lane = threadIdx.x & 3u;
+    const unsigned mask = 0xFu << (threadIdx.x & 28u);
+    typename F::E x, y, r;
+#pragma unroll
+    for (int k = 0; k < F::N; ++k) {
+      x.l[k] = lane == 0 ? a0.l[k] : (lane == 1 ? a1.l[k] : (lane == 2 ? a2.l[k] : a3.l[k]));
+      y.l[k] = lane == 0 ? b0.l[k] : (lane == 1 ? b1.l[k] : (lane == 2 ? b2.l[k] : b3.l[k]));
+    }
+    F::mul(r, x, y);
+#pragma unroll
+    for (int k = 0; k < F::N; ++k) {
+      o0.l[k] = __shfl_sync(mask, r.l[k], 0, 4);
+      o1.l[k] = __shfl_sync(mask, r.l[k], 1, 4);
+      o2.l[k] = __shfl_sync(mask, r.l[k], 2, 4);
+      o3.l[k] = __shfl_sync(mask, r.l[k], 3, 4);
+    }
+#else
+    SeqExec::mul4<F>(o0, o1, o2, o3, a0, b0, a1, b1, a2, b2, a3, b3);
+#endif
+  }
+  template <class F>
+  static B200_HD void mul2(typename F::E& o0, typename F::E& o1, const typename F::E& a0,
+                           const typename F::E& b0, const typename F::E& a1,
+                           const typename F::E& b1) {
+#ifdef __CUDA_ARCH__
+    const unsigned lane = threadIdx.x & 1u;
+    const unsigned mask = 0xFu << (threadIdx.x & 28u);
+    typename F::E x, y, r;
+#pragma unroll
+    for (int k = 0; k < F::N; ++k) {
+      x.l[k] = lane ? a1.l[k] : a0.l[k];
+      y.l[k] = lane ? b1.l[k] : b0.l[k];
+    }
+    F::mul(r, x, y);
+#pragma unroll
+    for (int k = 0; k < F::N; ++k) {
+      o0.l[k] = __shfl_sync(mask, r.l[k], 0, 4);
+      o1.l[k] = __shfl_sync(mask, r.l[k], 1, 4);
+    }
+#else
+    SeqExec::mul2<F>(o0, o1, a0, b0, a1, b1);
+#endif
+  }
+};
+
 // ================================================================================================
 // ed25519 / ristretto255
 // ================================================================================================
@@ -53,27 +135,23 @@ struct Ed25519 {
     r.Z = a.Z;
     F::neg(r.T, a.T);
   }
-  // r = a + b (unified; valid for doubling and identity operands)
-  static B200_HD void add(Point& r, const Point& a, const Point& b) {
-    fe A, B, C, D, E, Fv, G, H, t0, t1;
+  // r = a + b (unified; valid for doubling and identity operands); 4 + 1 + 4 multiplications
+  template <class X = SeqExec> static B200_HD void add(Point& r, const Point& a, const Point& b) {
+    fe A, B, C, D, E, Fv, G, H, t0, t1, t2, t3;
     F::sub(t0, a.Y, a.X);
     F::sub(t1, b.Y, b.X);
-    F::mul(A, t0, t1);
-    F::add(t0, a.Y, a.X);
-    F::add(t1, b.Y, b.X);
-    F::mul(B, t0, t1);
-    F::mul(C, a.T, b.T);
+    F::add(t2, a.Y, a.X);
+    F::add(t3, b.Y, b.X);
+    X::template mul4<F>(A, B, C, D, t0, t1, t2, t3, a.T, b.T, a.Z, b.Z);
     F::mul(C, C, F::constant([](int i) { return F25_D2(i); }));
-    F::mul(D, a.Z, b.Z);
     F::dbl(D, D);
     F::sub(E, B, A);
     F::sub(Fv, D, C);
     F::add(G, D, C);
     F::add(H, B, A);
-    F::mul(r.X, E, Fv);
-    F::mul(r.Y, G, H);
-    F::mul(r.T, E, H);
-    F::mul(r.Z, Fv, G);
+    Point o;
+    X::template mul4<F>(o.X, o.Y, o.T, o.Z, E, Fv, G, H, E, H, Fv, G);
+    r = o;
   }
   static B200_HD void point_to_gen(Gen& g, const Point& p) {
     F::add(g.YpX, p.Y, p.X);
@@ -95,6 +173,7 @@ struct Ed25519 {
   }
   // r = a +/- g in 8 multiplications; branch-free in `negate` (-g swaps Y+X / Y-X and negates 2dT)
   // so the lanes of a warp add generators of either sign in one pass
+  template <class X = SeqExec>
   static B200_HD void add_gen(Point& r, const Point& a, const Gen& g, bool negate) {
     fe A, B, C, D, E, Fv, G, H, t0, t1, qp, qm, qt, nt;
     F::select(qp, g.YpX, g.YmX, negate);
@@ -102,36 +181,28 @@ struct Ed25519 {
     F::neg(nt, g.T2d);
     F::select(qt, g.T2d, nt, negate);
     F::sub(t0, a.Y, a.X);
-    F::mul(A, t0, qm);
     F::add(t1, a.Y, a.X);
-    F::mul(B, t1, qp);
-    F::mul(C, a.T, qt);
-    F::mul(D, a.Z, g.Z2);
+    X::template mul4<F>(A, B, C, D, t0, qm, t1, qp, a.T, qt, a.Z, g.Z2);
     F::sub(E, B, A);
     F::sub(Fv, D, C);
     F::add(G, D, C);
     F::add(H, B, A);
-    F::mul(r.X, E, Fv);
-    F::mul(r.Y, G, H);
-    F::mul(r.T, E, H);
-    F::mul(r.Z, Fv, G);
+    Point o;
+    X::template mul4<F>(o.X, o.Y, o.T, o.Z, E, Fv, G, H, E, H, Fv, G);
+    r = o;
   }
-  static B200_HD void dbl(Point& r, const Point& a) {
-    fe A, B, C, E, Fv, G, H, t0;
-    F::sqr(A, a.X);
-    F::sqr(B, a.Y);
-    F::sqr(C, a.Z);
+  template <class X = SeqExec> static B200_HD void dbl(Point& r, const Point& a) {
+    fe A, B, C, E, Fv, G, H, t0, t1;
+    F::add(t0, a.X, a.Y);
+    X::template mul4<F>(A, B, C, t1, a.X, a.X, a.Y, a.Y, a.Z, a.Z, t0, t0);
     F::dbl(C, C);
     F::add(H, A, B);
-    F::add(t0, a.X, a.Y);
-    F::sqr(t0, t0);
-    F::sub(E, H, t0);
+    F::sub(E, H, t1);
     F::sub(G, A, B);
     F::add(Fv, C, G);
-    F::mul(r.X, E, Fv);
-    F::mul(r.Y, G, H);
-    F::mul(r.T, E, H);
-    F::mul(r.Z, Fv, G);
+    Point o;
+    X::template mul4<F>(o.X, o.Y, o.T, o.Z, E, Fv, G, H, E, H, Fv, G);
+    r = o;
   }
 
   // sxt_ristretto255 { u64 X[5], Y[5], Z[5], T[5] }
@@ -320,47 +391,46 @@ template <class FieldT, class CP> struct Weierstrass {
   }
   static B200_HD void mul_by_3b(fe& r, const fe& a) { CP::template mul_by_3b<F>(r, a); }
 
-  // RCB16 Algorithm 7 (a = 0)
-  static B200_HD void add(Point& r, const Point& p, const Point& q) {
-    fe t0, t1, t2, t3, t4, x3, y3, z3;
-    F::mul(t0, p.X, q.X);
-    F::mul(t1, p.Y, q.Y);
-    F::mul(t2, p.Z, q.Z);
+  // second half shared by Algorithms 7 and 8: six independent products
+  template <class X>
+  static B200_HD void finish_add(Point& r, const fe& t0, const fe& t1, const fe& t3, const fe& t4,
+                                 const fe& y3, const fe& z3) {
+    fe x3a, t2a, y3a, t1a, t0a, z3a;
+    X::template mul4<F>(x3a, t2a, y3a, t1a, t4, y3, t3, t1, y3, t0, t1, z3);
+    X::template mul2<F>(t0a, z3a, t0, t3, z3, t4);
+    F::sub(r.X, t2a, x3a);
+    F::add(r.Y, t1a, y3a);
+    F::add(r.Z, z3a, t0a);
+  }
+  // RCB16 Algorithm 7 (a = 0), 6 + 6 independent products
+  template <class X = SeqExec> static B200_HD void add(Point& r, const Point& p, const Point& q) {
+    fe t0, t1, t2, t3, t4, m3, m4, m5, u0, u1, v0, v1, x3, y3, z3;
     F::add(t3, p.X, p.Y);
     F::add(t4, q.X, q.Y);
-    F::mul(t3, t3, t4);
+    F::add(u0, p.Y, p.Z);
+    F::add(u1, q.Y, q.Z);
+    F::add(v0, p.X, p.Z);
+    F::add(v1, q.X, q.Z);
+    X::template mul4<F>(t0, t1, t2, m3, p.X, q.X, p.Y, q.Y, p.Z, q.Z, t3, t4);
+    X::template mul2<F>(m4, m5, u0, u1, v0, v1);
     F::add(t4, t0, t1);
-    F::sub(t3, t3, t4);
-    F::add(t4, p.Y, p.Z);
-    F::add(x3, q.Y, q.Z);
-    F::mul(t4, t4, x3);
+    F::sub(t3, m3, t4);
     F::add(x3, t1, t2);
-    F::sub(t4, t4, x3);
-    F::add(x3, p.X, p.Z);
-    F::add(y3, q.X, q.Z);
-    F::mul(x3, x3, y3);
+    F::sub(t4, m4, x3);
     F::add(y3, t0, t2);
-    F::sub(y3, x3, y3);
+    F::sub(y3, m5, y3);
     F::add(x3, t0, t0);
     F::add(t0, x3, t0);
     mul_by_3b(t2, t2);
     F::add(z3, t1, t2);
     F::sub(t1, t1, t2);
     mul_by_3b(y3, y3);
-    F::mul(x3, t4, y3);
-    F::mul(t2, t3, t1);
-    F::sub(x3, t2, x3);
-    F::mul(y3, y3, t0);
-    F::mul(t1, t1, z3);
-    F::add(y3, t1, y3);
-    F::mul(t0, t0, t3);
-    F::mul(z3, z3, t4);
-    F::add(z3, z3, t0);
-    r.X = x3;
-    r.Y = y3;
-    r.Z = z3;
+    Point o;
+    finish_add<X>(o, t0, t1, t3, t4, y3, z3);
+    r = o;
   }
   // RCB16 Algorithm 8 (a = 0): projective + affine; (0,0) generator = identity = no-op
+  template <class X = SeqExec>
   static B200_HD void add_gen(Point& r, const Point& p, const Gen& g, bool negate) {
     if (gen_is_identity(g)) {
       r = p;
@@ -369,17 +439,14 @@ template <class FieldT, class CP> struct Weierstrass {
     fe qy, ny;
     F::neg(ny, g.y);
     F::select(qy, g.y, ny, negate);
-    fe t0, t1, t2, t3, t4, x3, y3, z3;
-    F::mul(t0, p.X, g.x);
-    F::mul(t1, p.Y, qy);
+    fe t0, t1, t2, t3, t4, m3, x3, y3, z3;
     F::add(t3, g.x, qy);
     F::add(t4, p.X, p.Y);
-    F::mul(t3, t3, t4);
-    F::add(t4, t0, t1);
-    F::sub(t3, t3, t4);
-    F::mul(t4, qy, p.Z);
-    F::add(t4, t4, p.Y);
+    X::template mul4<F>(t0, t1, m3, t2, p.X, g.x, p.Y, qy, t3, t4, qy, p.Z);
     F::mul(y3, g.x, p.Z);
+    F::add(t4, t0, t1);
+    F::sub(t3, m3, t4);
+    F::add(t4, t2, p.Y);
     F::add(y3, y3, p.X);
     F::add(x3, t0, t0);
     F::add(t0, x3, t0);
@@ -387,18 +454,9 @@ template <class FieldT, class CP> struct Weierstrass {
     F::add(z3, t1, t2);
     F::sub(t1, t1, t2);
     mul_by_3b(y3, y3);
-    F::mul(x3, t4, y3);
-    F::mul(t2, t3, t1);
-    F::sub(x3, t2, x3);
-    F::mul(y3, y3, t0);
-    F::mul(t1, t1, z3);
-    F::add(y3, t1, y3);
-    F::mul(t0, t0, t3);
-    F::mul(z3, z3, t4);
-    F::add(z3, z3, t0);
-    r.X = x3;
-    r.Y = y3;
-    r.Z = z3;
+    Point o;
+    finish_add<X>(o, t0, t1, t3, t4, y3, z3);
+    r = o;
   }
   static B200_HD void gen_to_point(Point& r, const Gen& g, bool negate) {
     if (gen_is_identity(g)) {
@@ -411,30 +469,24 @@ template <class FieldT, class CP> struct Weierstrass {
     F::select(r.Y, g.y, ny, negate);
     r.Z = F::one();
   }
-  // RCB16 Algorithm 9 (a = 0)
-  static B200_HD void dbl(Point& r, const Point& p) {
-    fe t0, t1, t2, x3, y3, z3;
-    F::sqr(t0, p.Y);
+  // RCB16 Algorithm 9 (a = 0), 4 + 4 independent products
+  template <class X = SeqExec> static B200_HD void dbl(Point& r, const Point& p) {
+    fe t0, t1, t2, txy, x3, y3, z3, xa, xb;
+    X::template mul4<F>(t0, t1, t2, txy, p.Y, p.Y, p.Y, p.Z, p.Z, p.Z, p.X, p.Y);
     F::add(z3, t0, t0);
     F::add(z3, z3, z3);
     F::add(z3, z3, z3);
-    F::mul(t1, p.Y, p.Z);
-    F::sqr(t2, p.Z);
     mul_by_3b(t2, t2);
-    F::mul(x3, t2, z3);
     F::add(y3, t0, t2);
-    F::mul(z3, t1, z3);
-    F::add(t1, t2, t2);
-    F::add(t2, t1, t2);
-    F::sub(t0, t0, t2);
-    F::mul(y3, t0, y3);
-    F::add(y3, x3, y3);
-    F::mul(t1, p.X, p.Y);
-    F::mul(x3, t0, t1);
-    F::add(x3, x3, x3);
-    r.X = x3;
-    r.Y = y3;
-    r.Z = z3;
+    fe t22, t23;
+    F::add(t22, t2, t2);
+    F::add(t23, t22, t2);
+    F::sub(t0, t0, t23);
+    Point o;
+    X::template mul4<F>(xa, o.Z, y3, xb, t2, z3, t1, z3, t0, y3, t0, txy);
+    F::add(o.Y, xa, y3);
+    F::add(o.X, xb, xb);
+    r = o;
   }
 
   // affine ABI struct {u64 X[N/2]; u64 Y[N/2]; u8 infinity} (cg1t/cn1t/cgkt::element_affine)

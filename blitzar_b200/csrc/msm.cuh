@@ -177,8 +177,7 @@ struct ScatterBody {
   const u64* col_start;
   u32 ncols, c, nbuckets;
   u32* cursor;  // exclusive offsets, consumed
-  u32* entry_key;
-  u32* entry_idx;
+  u64* entries;  // (key << 32) | (generator index << 1) | negate
   B200_HD void operator()(u64 tid) const {
     u32 j = 0;
     while (j + 1 < ncols && tid >= col_start[j + 1])
@@ -189,13 +188,11 @@ struct ScatterBody {
     bool neg;
     load_scalar_bits(v, neg, col, i);
     u32* cur = cursor;
-    u32* ek = entry_key;
-    u32* ei = entry_idx;
+    u64* en = entries;
     u32 ii = (u32)i;
-    for_each_digit(v, neg, col, c, nbuckets, [cur, ek, ei, ii](u32 key, bool negate) {
+    for_each_digit(v, neg, col, c, nbuckets, [cur, en, ii](u32 key, bool negate) {
       u32 pos = B200_ATOMIC_ADD(&cur[key], 1u);
-      ek[pos] = key;
-      ei[pos] = (ii << 1) | (negate ? 1u : 0u);
+      en[pos] = ((u64)key << 32) | (u64)((ii << 1) | (negate ? 1u : 0u));
     });
   }
 };
@@ -269,11 +266,11 @@ template <class C> struct FillIdentityBody {
 // strictly inside the chunk are complete and go straight to buckets[key]; the first and last
 // segment may continue in the neighbouring chunks, so they are emitted as pieces (2 per chunk,
 // keys stay sorted) for the next, K/2-times smaller, level. The final level writes everything.
-template <class C, bool kGather> struct AccumulateBody {
+template <class C, bool kGather, class X = SeqExec> struct AccumulateBody {
   static constexpr int kBlock = 128;
   typedef typename C::Point Point;
-  const u32* keys;
-  const u32* idx;                  // level 1: (generator index << 1) | negate
+  const u32* keys;                 // level >= 2
+  const u64* entries;              // level 1: (key << 32) | (generator index << 1) | negate
   const typename C::Gen* gens;     // level 1
   const Point* pieces;             // level >= 2
   const u32* m_ptr;                // number of entries at this level (device)
@@ -284,49 +281,56 @@ template <class C, bool kGather> struct AccumulateBody {
   Point* out_pieces;
   u32* out_m_ptr;
 
+  B200_HD u32 key_at(u64 i) const { return kGather ? (u32)(entries[i] >> 32) : keys[i]; }
   B200_HD void fetch(Point& acc, u64 i, bool first) const {
     if (kGather) {
-      u32 e = idx[i];
+      u32 e = (u32)entries[i];
       if (first)
         C::gen_to_point(acc, gens[e >> 1], e & 1u);
       else
-        C::add_gen(acc, acc, gens[e >> 1], e & 1u);
+        C::template add_gen<X>(acc, acc, gens[e >> 1], e & 1u);
     } else {
       if (first)
         acc = pieces[i];
       else
-        C::add(acc, acc, pieces[i]);
+        C::template add<X>(acc, acc, pieces[i]);
     }
   }
-  B200_HD void operator()(u64 t) const {
+  B200_HD void operator()(u64 tid) const {
+    const u64 t = tid / X::kLanes;
+    const bool writer = (tid % X::kLanes) == 0;
     const u64 M = *m_ptr;
     const u64 T = (M + K - 1) / K;
-    if (t == 0 && out_m_ptr)
+    if (tid == 0 && out_m_ptr)
       *out_m_ptr = final_level ? 0u : (u32)(2 * T);
     u64 b = t * K;
     if (b >= M)
       return;
     u64 e = b + K < M ? b + K : M;
-    u32 cur = keys[b];
+    u32 cur = key_at(b);
     Point acc;
     fetch(acc, b, true);
     bool first_seg = true;
     for (u64 i = b + 1; i < e; ++i) {
-      u32 k = keys[i];
+      u32 k = key_at(i);
       if (k == cur) {
         fetch(acc, i, false);
       } else {
-        if (final_level || !first_seg) {
-          buckets[cur] = acc;
-        } else {
-          out_keys[2 * t] = cur;
-          out_pieces[2 * t] = acc;
+        if (writer) {
+          if (final_level || !first_seg) {
+            buckets[cur] = acc;
+          } else {
+            out_keys[2 * t] = cur;
+            out_pieces[2 * t] = acc;
+          }
         }
         first_seg = false;
         cur = k;
         fetch(acc, i, true);
       }
     }
+    if (!writer)
+      return;
     if (final_level) {
       buckets[cur] = acc;
     } else if (first_seg) {  // single-segment chunk: pad the tail slot with the identity
@@ -345,7 +349,7 @@ template <class C, bool kGather> struct AccumulateBody {
 // m entries by groups of g: Xout[k] = g * sum_r X[gk+r], Cout[k] = sum_r r*X[gk+r] + sum_r Cin[gk+r]
 // (first level: weights r+1, no Cin, because bucket id = index + 1). Repeating until m == 1 leaves
 // the window sum in Cout[0].
-template <class C> struct ReduceBody {
+template <class C, class Ex = SeqExec> struct ReduceBody {
   static constexpr int kBlock = 64;
   typedef typename C::Point Point;
   const Point* X;
@@ -355,15 +359,19 @@ template <class C> struct ReduceBody {
   Point* Cout;
   const u32* bucket_end;  // cursor array after the scatter: end offset of every bucket
   u32 nbuckets;
-  B200_HD void operator()(u64 t) const {
+  B200_HD void operator()(u64 tid) const {
+    const u64 t = tid / Ex::kLanes;
+    const bool writer = (tid % Ex::kLanes) == 0;
     const u32 m_out = m_in / g;
     const u32 w = (u32)(t / m_out), k = (u32)(t % m_out);
     // empty window: nothing was scattered into any of its buckets
     u32 lo = w ? bucket_end[(u64)w * nbuckets - 1] : 0u;
     u32 hi = bucket_end[(u64)(w + 1) * nbuckets - 1];
     if (lo == hi) {
-      Xout[t] = C::identity();
-      Cout[t] = C::identity();
+      if (writer) {
+        Xout[t] = C::identity();
+        Cout[t] = C::identity();
+      }
       return;
     }
     const Point* x = X + (u64)w * m_in + (u64)k * g;
@@ -376,43 +384,49 @@ template <class C> struct ReduceBody {
         acc = C::identity();
     }
     for (u32 r = g - 1; r-- > 0;) {
-      C::add(run, run, x[r]);
+      C::template add<Ex>(run, run, x[r]);
       if (r > 0 || !Cin)
-        C::add(acc, acc, run);
+        C::template add<Ex>(acc, acc, run);
     }
     if (Cin) {
       const Point* cin = Cin + (u64)w * m_in + (u64)k * g;
       for (u32 r = 0; r < g; ++r)
-        C::add(acc, acc, cin[r]);
+        C::template add<Ex>(acc, acc, cin[r]);
     }
     for (u32 i = 0; i < log2g; ++i)
-      C::dbl(run, run);
-    Xout[t] = run;
-    Cout[t] = acc;
+      C::template dbl<Ex>(run, run);
+    if (writer) {
+      Xout[t] = run;
+      Cout[t] = acc;
+    }
   }
 };
 
 // Horner over a column's windows: out = sum_w 2^(c*w) * S[w]
-template <class C> struct CombineBody {
+template <class C, class X = SeqExec> struct CombineBody {
   static constexpr int kBlock = 32;
   typedef typename C::Point Point;
   const Point* S;  // one per window (flattened)
   const ColumnDesc* cols;
   u32 c;
   Point* out;
-  B200_HD void operator()(u64 j) const {
+  B200_HD void operator()(u64 tid) const {
+    const u64 j = tid / X::kLanes;
+    const bool writer = (tid % X::kLanes) == 0;
     const ColumnDesc col = cols[j];
     if (col.num_windows == 0 || col.n == 0) {
-      out[j] = C::identity();
+      if (writer)
+        out[j] = C::identity();
       return;
     }
     Point acc = S[col.first_window + col.num_windows - 1];
     for (u32 w = col.num_windows - 1; w-- > 0;) {
       for (u32 i = 0; i < c; ++i)
-        C::dbl(acc, acc);
-      C::add(acc, acc, S[col.first_window + w]);
+        C::template dbl<X>(acc, acc);
+      C::template add<X>(acc, acc, S[col.first_window + w]);
     }
-    out[j] = acc;
+    if (writer)
+      out[j] = acc;
   }
 };
 
@@ -497,6 +511,7 @@ struct MsmOptions {
   u32 chunkn = 8;       // chunk length of the cascade levels
   u32 reduce_g1 = 8;    // bucket-reduction group size, first level (power of two)
   u32 reduce_gn = 8;    // bucket-reduction group size, later levels (power of two)
+  u64 quad_threshold = 32768;  // launches with at most this many logical threads run 4 lanes each
 };
 
 // Computes out[j] = sum_i scalar(j,i) * G_i for every column j. `cols` are host descriptors whose
@@ -554,10 +569,9 @@ void msm_run(stream_t s, const typename C::Gen* gens, std::vector<ColumnDesc> co
   u32* d_m = (u32*)dev_alloc(16 * sizeof(u32), s);
   copy_d2d(d_m, d_counts + nkeys, sizeof(u32), s);
 
-  u32* d_keys = (u32*)dev_alloc(max_entries * sizeof(u32), s);
-  u32* d_idx = (u32*)dev_alloc(max_entries * sizeof(u32), s);
-  launch(ScatterBody{d_cols, d_col_start, ncols, c, nbuckets, d_counts, d_keys, d_idx},
-         total_terms, s);
+  u64* d_entries = (u64*)dev_alloc(max_entries * sizeof(u64), s);
+  launch(ScatterBody{d_cols, d_col_start, ncols, c, nbuckets, d_counts, d_entries}, total_terms,
+         s);
   // d_counts[k] is now the END offset of bucket k
 
   Point* d_buckets = (Point*)dev_alloc(nkeys * sizeof(Point), s);
@@ -569,7 +583,7 @@ void msm_run(stream_t s, const typename C::Gen* gens, std::vector<ColumnDesc> co
     const u32 chunk1 = opt.chunk1 < 4 ? 4u : opt.chunk1, chunkn = opt.chunkn < 4 ? 4u : opt.chunkn;
     u64 m_max = max_entries;
     u32 K = chunk1;
-    const u32* lvl_keys = d_keys;
+    const u32* lvl_keys = nullptr;
     const Point* lvl_pieces = nullptr;
     u32* m_ptr = d_m;
     std::vector<void*> to_free;
@@ -589,11 +603,16 @@ void msm_run(stream_t s, const typename C::Gen* gens, std::vector<ColumnDesc> co
       }
       if (first) {
         KernelTimer::get().begin(s);
-        launch(AccumulateBody<C, true>{lvl_keys, d_idx, gens, nullptr, m_ptr, K,
+        launch(AccumulateBody<C, true>{nullptr, d_entries, gens, nullptr, m_ptr, K,
                                        final_level ? 1u : 0u, d_buckets, out_keys, out_pieces,
                                        out_m},
                T, s);
         KernelTimer::get().end(s);
+      } else if (T <= opt.quad_threshold) {
+        launch(AccumulateBody<C, false, QuadExec>{lvl_keys, nullptr, nullptr, lvl_pieces, m_ptr, K,
+                                                  final_level ? 1u : 0u, d_buckets, out_keys,
+                                                  out_pieces, out_m},
+               T * QuadExec::kLanes, s);
       } else {
         launch(AccumulateBody<C, false>{lvl_keys, nullptr, nullptr, lvl_pieces, m_ptr, K,
                                         final_level ? 1u : 0u, d_buckets, out_keys, out_pieces,
@@ -613,8 +632,7 @@ void msm_run(stream_t s, const typename C::Gen* gens, std::vector<ColumnDesc> co
     for (void* p : to_free)
       dev_free(p, s);
   }
-  dev_free(d_keys, s);
-  dev_free(d_idx, s);
+  dev_free(d_entries, s);
 
   // bucket reduction: nbuckets -> 1 per window
   Point* d_S = nullptr;
@@ -637,8 +655,12 @@ void msm_run(stream_t s, const typename C::Gen* gens, std::vector<ColumnDesc> co
       u32 m_out = m / g;
       Point* Xout = (Point*)dev_alloc((u64)total_windows * m_out * sizeof(Point), s);
       Point* Cout = (Point*)dev_alloc((u64)total_windows * m_out * sizeof(Point), s);
-      launch(ReduceBody<C>{X, Cin, m, g, log2g, Xout, Cout, d_counts, nbuckets},
-             (u64)total_windows * m_out, s);
+      if ((u64)total_windows * m_out <= opt.quad_threshold)
+        launch(ReduceBody<C, QuadExec>{X, Cin, m, g, log2g, Xout, Cout, d_counts, nbuckets},
+               (u64)total_windows * m_out * QuadExec::kLanes, s);
+      else
+        launch(ReduceBody<C>{X, Cin, m, g, log2g, Xout, Cout, d_counts, nbuckets},
+               (u64)total_windows * m_out, s);
       to_free.push_back(Xout);
       if (m_out > 1)
         to_free.push_back(Cout);
@@ -652,7 +674,10 @@ void msm_run(stream_t s, const typename C::Gen* gens, std::vector<ColumnDesc> co
     for (void* p : to_free)
       dev_free(p, s);
   }
-  launch(CombineBody<C>{d_S, d_cols, c, out}, ncols, s);
+  if (ncols <= opt.quad_threshold)
+    launch(CombineBody<C, QuadExec>{d_S, d_cols, c, out}, (u64)ncols * QuadExec::kLanes, s);
+  else
+    launch(CombineBody<C>{d_S, d_cols, c, out}, ncols, s);
   dev_free(d_S, s);
   dev_free(d_buckets, s);
   dev_free(d_counts, s);
