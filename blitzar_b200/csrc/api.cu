@@ -14,8 +14,7 @@
 #include <string>
 #include <vector>
 
-#define B200_EXTERN_CURVES
-#include "engine.cuh"
+#include "engine_api.cuh"
 
 using namespace b200;
 
@@ -25,7 +24,7 @@ struct State {
   bool initialized = false;
   int device = -1;
   cudaStream_t stream = nullptr;
-  Ed25519::Gen* builtin = nullptr;  // g(0..num_builtin) device-resident
+  void* builtin = nullptr;  // g(0..num_builtin) device-resident, ed25519 generator layout
   uint64_t num_builtin = 0;
   MsmOptions opt;
 };
@@ -63,25 +62,54 @@ void require_init(const char* fn) {
   B200_CUDA(cudaSetDevice(g_state.device));
 }
 
+const CurveVTable& vt(unsigned curve_id) {
+  switch (curve_id) {
+  case SXT_CURVE_RISTRETTO255:
+    return kVTableEd25519;
+  case SXT_CURVE_BLS_381:
+    return kVTableBls12381;
+  case SXT_CURVE_BN_254:
+    return kVTableBn254;
+  case SXT_CURVE_GRUMPKIN:
+    return kVTableGrumpkin;
+  default:
+    die("unsupported curve id", __FILE__, __LINE__);
+  }
+}
+
+// validates like cbindings/pedersen.cc:44-68 and returns the longest column
+uint64_t longest_column(const sxt_sequence_descriptor* d, uint32_t num) {
+  B200_REQUIRE(d != nullptr, "descriptors == nullptr");
+  uint64_t longest = 0;
+  for (uint32_t i = 0; i < num; ++i) {
+    B200_REQUIRE(d[i].n == 0 || d[i].data != nullptr, "descriptor.n > 0 with data == nullptr");
+    B200_REQUIRE(d[i].element_nbytes != 0 && d[i].element_nbytes <= 32,
+                 "descriptor.element_nbytes must be in 1..32");
+    longest = longest < d[i].n ? d[i].n : longest;
+  }
+  return longest;
+}
+
 // host-pointer commitments: H2D, device MSM, D2H
-template <class C>
-void commit_host(void* commitments, uint32_t num, const sxt_sequence_descriptor* d,
-                 const void* generators, uint64_t offset_generators, const char* fn) {
+void commit_host(unsigned curve_id, void* commitments, uint32_t num,
+                 const sxt_sequence_descriptor* d, const void* generators,
+                 uint64_t offset_generators, const char* fn) {
   if (num == 0)
     return;
   std::lock_guard<std::mutex> lock(g_mutex);
   require_init(fn);
   B200_REQUIRE(commitments != nullptr, "commitments == nullptr");
+  const CurveVTable& V = vt(curve_id);
   cudaStream_t s = g_state.stream;
-  uint64_t n = check_descriptors(d, num);
-  if (C::kCurveId != kRistretto255)
+  uint64_t n = longest_column(d, num);
+  if (curve_id != SXT_CURVE_RISTRETTO255)
     B200_REQUIRE(generators != nullptr, "generators == nullptr");
   size_t total_scalar_bytes = 0;
   for (uint32_t i = 0; i < num; ++i)
     total_scalar_bytes += (size_t)d[i].n * d[i].element_nbytes + 32;
-  DevBuf<unsigned char> raw_gens(generators ? n * C::kAbiGenBytes : 1, s);
+  DevBuf<unsigned char> raw_gens(generators ? n * V.abi_gen_bytes : 1, s);
   DevBuf<unsigned char> scal(total_scalar_bytes, s);
-  DevBuf<unsigned char> out(num * C::kAbiCommitBytes, s);
+  DevBuf<unsigned char> out((size_t)num * V.abi_commit_bytes, s);
   std::vector<sxt_sequence_descriptor> dd(d, d + num);
   size_t off = 0;
   for (uint32_t i = 0; i < num; ++i) {
@@ -91,28 +119,28 @@ void commit_host(void* commitments, uint32_t num, const sxt_sequence_descriptor*
     off += (bytes + 31) & ~(size_t)31;
   }
   if (generators)
-    copy_h2d(raw_gens.p, generators, n * C::kAbiGenBytes, s);
-  CurveOps<C>::commit_device(ctx(), out.p, nullptr, num, dd.data(), generators ? raw_gens.p : nullptr,
-                   offset_generators);
-  copy_d2h(commitments, out.p, num * C::kAbiCommitBytes, s);
+    copy_h2d(raw_gens.p, generators, n * V.abi_gen_bytes, s);
+  V.commit_device(ctx(), out.p, nullptr, num, dd.data(), generators ? raw_gens.p : nullptr,
+                  offset_generators);
+  copy_d2h(commitments, out.p, (size_t)num * V.abi_commit_bytes, s);
   stream_sync(s);
 }
 
-template <class C> Handle* handle_new(const void* generators, unsigned n) {
+Handle* handle_new(unsigned curve_id, const void* generators, unsigned n) {
+  const CurveVTable& V = vt(curve_id);
   cudaStream_t s = g_state.stream;
-  Handle* h = new Handle{C::kCurveId, n, nullptr};
-  B200_CUDA(cudaMalloc(&h->gens, (n ? n : 1) * sizeof(typename C::Gen)));
+  Handle* h = new Handle{curve_id, n, nullptr};
+  B200_CUDA(cudaMalloc(&h->gens, (size_t)(n ? n : 1) * V.gen_bytes));
   if (n) {
     B200_REQUIRE(generators != nullptr, "generators == nullptr");
-    DevBuf<unsigned char> raw((size_t)n * C::kAbiProjBytes, s);
-    copy_h2d(raw.p, generators, (size_t)n * C::kAbiProjBytes, s);
-    CurveOps<C>::ingest_projective(ctx(), raw.p, h->gens, n);
+    DevBuf<unsigned char> raw((size_t)n * V.abi_proj_bytes, s);
+    copy_h2d(raw.p, generators, (size_t)n * V.abi_proj_bytes, s);
+    V.ingest_projective(ctx(), raw.p, h->gens, n);
     stream_sync(s);
   }
   return h;
 }
 
-template <class C>
 void fixed_host(void* res, const Handle* h, int mode, unsigned element_num_bytes,
                 const unsigned* bit_table, const unsigned* lengths, unsigned num_outputs,
                 unsigned n, const uint8_t* scalars) {
@@ -132,27 +160,13 @@ void fixed_host(void* res, const Handle* h, int mode, unsigned element_num_bytes
   size_t bytes = (size_t)((row_bits + 7) / 8) * rows;
   B200_REQUIRE(bytes == 0 || scalars != nullptr, "scalars == nullptr");
   DevBuf<unsigned char> scal(bytes + 64, s);
-  DevBuf<unsigned char> out((size_t)num_outputs * C::kAbiProjBytes, s);
+  const CurveVTable& V = vt(h->curve_id);
+  DevBuf<unsigned char> out((size_t)num_outputs * V.abi_proj_bytes, s);
   copy_h2d(scal.p, scalars, bytes, s);
-  CurveOps<C>::fixed_device(ctx(), out.p, nullptr, h, mode, element_num_bytes, bit_table, lengths, num_outputs,
-                  rows, scal.p);
-  copy_d2h(res, out.p, (size_t)num_outputs * C::kAbiProjBytes, s);
+  V.fixed_device(ctx(), out.p, nullptr, h, mode, element_num_bytes, bit_table, lengths,
+                 num_outputs, rows, scal.p);
+  copy_d2h(res, out.p, (size_t)num_outputs * V.abi_proj_bytes, s);
   stream_sync(s);
-}
-
-template <class F> auto dispatch(unsigned curve_id, F f) {
-  switch (curve_id) {
-  case kRistretto255:
-    return f(Ed25519{});
-  case kBls12381:
-    return f(Bls12381G1{});
-  case kBn254:
-    return f(Bn254G1{});
-  case kGrumpkin:
-    return f(GrumpkinG{});
-  default:
-    die("unsupported curve id", __FILE__, __LINE__);
-  }
 }
 
 const uint32_t kHandleMagic = 0x44483242u;  // "B2HD"
@@ -193,7 +207,7 @@ int sxt_init(const struct sxt_config* config) {
   g_state.initialized = true;
   uint64_t np = config->num_precomputed_generators;
   if (np) {
-    B200_CUDA(cudaMalloc(&g_state.builtin, np * sizeof(Ed25519::Gen)));
+    B200_CUDA(cudaMalloc(&g_state.builtin, np * kVTableEd25519.gen_bytes));
     launch_builtin_generators(ctx(), g_state.builtin, 0, np);
     stream_sync(g_state.stream);
     g_state.num_builtin = np;
@@ -205,34 +219,34 @@ void sxt_curve25519_compute_pedersen_commitments(struct sxt_ristretto255_compres
                                                  uint32_t num_sequences,
                                                  const struct sxt_sequence_descriptor* descriptors,
                                                  uint64_t offset_generators) {
-  commit_host<Ed25519>(commitments, num_sequences, descriptors, nullptr, offset_generators,
-                       "sxt_curve25519_compute_pedersen_commitments");
+  commit_host(SXT_CURVE_RISTRETTO255, commitments, num_sequences, descriptors, nullptr,
+              offset_generators, "sxt_curve25519_compute_pedersen_commitments");
 }
 void sxt_curve25519_compute_pedersen_commitments_with_generators(
     struct sxt_ristretto255_compressed* commitments, uint32_t num_sequences,
     const struct sxt_sequence_descriptor* descriptors, const struct sxt_ristretto255* generators) {
   // generators == nullptr falls back to the built-in generators at offset 0, as the reference does
   // (cbindings/pedersen.cc:90-96)
-  commit_host<Ed25519>(commitments, num_sequences, descriptors, generators, 0,
-                       "sxt_curve25519_compute_pedersen_commitments_with_generators");
+  commit_host(SXT_CURVE_RISTRETTO255, commitments, num_sequences, descriptors, generators, 0,
+              "sxt_curve25519_compute_pedersen_commitments_with_generators");
 }
 void sxt_bls12_381_g1_compute_pedersen_commitments_with_generators(
     struct sxt_bls12_381_g1_compressed* commitments, uint32_t num_sequences,
     const struct sxt_sequence_descriptor* descriptors, const struct sxt_bls12_381_g1* generators) {
-  commit_host<Bls12381G1>(commitments, num_sequences, descriptors, generators, 0,
-                          "sxt_bls12_381_g1_compute_pedersen_commitments_with_generators");
+  commit_host(SXT_CURVE_BLS_381, commitments, num_sequences, descriptors, generators, 0,
+              "sxt_bls12_381_g1_compute_pedersen_commitments_with_generators");
 }
 void sxt_bn254_g1_uncompressed_compute_pedersen_commitments_with_generators(
     struct sxt_bn254_g1* commitments, uint32_t num_sequences,
     const struct sxt_sequence_descriptor* descriptors, const struct sxt_bn254_g1* generators) {
-  commit_host<Bn254G1>(commitments, num_sequences, descriptors, generators, 0,
-                       "sxt_bn254_g1_uncompressed_compute_pedersen_commitments_with_generators");
+  commit_host(SXT_CURVE_BN_254, commitments, num_sequences, descriptors, generators, 0,
+              "sxt_bn254_g1_uncompressed_compute_pedersen_commitments_with_generators");
 }
 void sxt_grumpkin_uncompressed_compute_pedersen_commitments_with_generators(
     struct sxt_grumpkin* commitments, uint32_t num_sequences,
     const struct sxt_sequence_descriptor* descriptors, const struct sxt_grumpkin* generators) {
-  commit_host<GrumpkinG>(commitments, num_sequences, descriptors, generators, 0,
-                         "sxt_grumpkin_uncompressed_compute_pedersen_commitments_with_generators");
+  commit_host(SXT_CURVE_GRUMPKIN, commitments, num_sequences, descriptors, generators, 0,
+              "sxt_grumpkin_uncompressed_compute_pedersen_commitments_with_generators");
 }
 
 int sxt_ristretto255_get_generators(struct sxt_ristretto255* generators, uint64_t num_generators,
@@ -243,16 +257,17 @@ int sxt_ristretto255_get_generators(struct sxt_ristretto255* generators, uint64_
     return 0;
   if (generators == nullptr)
     return 1;
+  const CurveVTable& V = kVTableEd25519;
   cudaStream_t s = g_state.stream;
-  DevBuf<Ed25519::Gen> gens(num_generators, s);
-  const Ed25519::Gen* src = gens.p;
+  DevBuf<unsigned char> gens(num_generators * V.gen_bytes, s);
+  const void* src = gens.p;
   if (offset_generators + num_generators <= g_state.num_builtin)
-    src = g_state.builtin + offset_generators;
+    src = (const unsigned char*)g_state.builtin + offset_generators * V.gen_bytes;
   else
     launch_builtin_generators(ctx(), gens.p, offset_generators, num_generators);
-  DevBuf<unsigned char> out(num_generators * Ed25519::kAbiProjBytes, s);
-  CurveOps<Ed25519>::gens_to_projective(ctx(), src, out.p, num_generators);
-  copy_d2h(generators, out.p, num_generators * Ed25519::kAbiProjBytes, s);
+  DevBuf<unsigned char> out(num_generators * V.abi_proj_bytes, s);
+  V.gens_to_projective(ctx(), src, out.p, num_generators);
+  copy_d2h(generators, out.p, num_generators * V.abi_proj_bytes, s);
   stream_sync(s);
   return 0;
 }
@@ -262,16 +277,17 @@ int sxt_curve25519_get_one_commit(struct sxt_ristretto255* one_commit, uint64_t 
   require_init("sxt_curve25519_get_one_commit");
   B200_REQUIRE(one_commit != nullptr, "one_commit == nullptr");
   B200_REQUIRE(n < (1ull << 31), "n too large");
+  const CurveVTable& V = kVTableEd25519;
   cudaStream_t s = g_state.stream;
   // sum of the first n built-in generators = MSM with all-one 1-byte scalars
   DevBuf<unsigned char> ones(n + 32, s);
   B200_CUDA(cudaMemsetAsync(ones.p, 1, n + 32, s));
   sxt_sequence_descriptor d{1, n, ones.p, 0};
-  DevBuf<Ed25519::Point> pt(1, s);
-  DevBuf<unsigned char> out(Ed25519::kAbiProjBytes, s);
-  CurveOps<Ed25519>::commit_device(ctx(), nullptr, pt.p, 1, &d, nullptr, 0);
-  CurveOps<Ed25519>::store(ctx(), pt.p, out.p, 1, false);
-  copy_d2h(one_commit, out.p, Ed25519::kAbiProjBytes, s);
+  DevBuf<unsigned char> pt(V.point_bytes, s);
+  DevBuf<unsigned char> out(V.abi_proj_bytes, s);
+  V.commit_device(ctx(), nullptr, pt.p, 1, &d, nullptr, 0);
+  V.store(ctx(), pt.p, out.p, 1, false);
+  copy_d2h(one_commit, out.p, V.abi_proj_bytes, s);
   stream_sync(s);
   return 0;
 }
@@ -303,8 +319,7 @@ struct sxt_multiexp_handle* sxt_multiexp_handle_new(unsigned curve_id, const voi
                                                     unsigned n) {
   std::lock_guard<std::mutex> lock(g_mutex);
   require_init("sxt_multiexp_handle_new");
-  Handle* h = dispatch(curve_id, [&](auto c) { return handle_new<decltype(c)>(generators, n); });
-  return reinterpret_cast<sxt_multiexp_handle*>(h);
+  return reinterpret_cast<sxt_multiexp_handle*>(handle_new(curve_id, generators, n));
 }
 
 void sxt_multiexp_handle_free(struct sxt_multiexp_handle* handle) {
@@ -327,23 +342,20 @@ void sxt_multiexp_handle_write_to_file(const struct sxt_multiexp_handle* handle,
   require_init("sxt_multiexp_handle_write_to_file");
   const Handle* h = reinterpret_cast<const Handle*>(handle);
   B200_REQUIRE(h && filename, "null handle or filename");
+  const CurveVTable& V = vt(h->curve_id);
   cudaStream_t s = g_state.stream;
-  dispatch(h->curve_id, [&](auto c) {
-    typedef decltype(c) C;
-    size_t bytes = (size_t)h->n * C::kAbiProjBytes;
-    DevBuf<unsigned char> out(bytes + 16, s);
-    CurveOps<C>::gens_to_projective(ctx(), h->gens, out.p, h->n);
-    std::vector<unsigned char> host(bytes);
-    copy_d2h(host.data(), out.p, bytes, s);
-    stream_sync(s);
-    FILE* f = std::fopen(filename, "wb");
-    B200_REQUIRE(f != nullptr, "cannot open handle file for writing");
-    uint32_t hdr[4] = {kHandleMagic, 1u, h->curve_id, h->n};
-    B200_REQUIRE(std::fwrite(hdr, sizeof(hdr), 1, f) == 1, "short write");
-    B200_REQUIRE(bytes == 0 || std::fwrite(host.data(), bytes, 1, f) == 1, "short write");
-    std::fclose(f);
-    return 0;
-  });
+  size_t bytes = (size_t)h->n * V.abi_proj_bytes;
+  DevBuf<unsigned char> out(bytes + 16, s);
+  V.gens_to_projective(ctx(), h->gens, out.p, h->n);
+  std::vector<unsigned char> host(bytes);
+  copy_d2h(host.data(), out.p, bytes, s);
+  stream_sync(s);
+  FILE* f = std::fopen(filename, "wb");
+  B200_REQUIRE(f != nullptr, "cannot open handle file for writing");
+  uint32_t hdr[4] = {kHandleMagic, 1u, h->curve_id, h->n};
+  B200_REQUIRE(std::fwrite(hdr, sizeof(hdr), 1, f) == 1, "short write");
+  B200_REQUIRE(bytes == 0 || std::fwrite(host.data(), bytes, 1, f) == 1, "short write");
+  std::fclose(f);
 }
 
 struct sxt_multiexp_handle* sxt_multiexp_handle_new_from_file(unsigned curve_id,
@@ -357,15 +369,11 @@ struct sxt_multiexp_handle* sxt_multiexp_handle_new_from_file(unsigned curve_id,
   B200_REQUIRE(std::fread(hdr, sizeof(hdr), 1, f) == 1, "short handle file");
   B200_REQUIRE(hdr[0] == kHandleMagic && hdr[1] == 1u, "not a blitzar_b200 handle file");
   B200_REQUIRE(hdr[2] == curve_id, "handle file is for another curve");
-  Handle* h = dispatch(curve_id, [&](auto c) {
-    typedef decltype(c) C;
-    size_t bytes = (size_t)hdr[3] * C::kAbiProjBytes;
-    std::vector<unsigned char> host(bytes);
-    B200_REQUIRE(bytes == 0 || std::fread(host.data(), bytes, 1, f) == 1, "short handle file");
-    return handle_new<C>(host.data(), hdr[3]);
-  });
+  size_t bytes = (size_t)hdr[3] * vt(curve_id).abi_proj_bytes;
+  std::vector<unsigned char> host(bytes);
+  B200_REQUIRE(bytes == 0 || std::fread(host.data(), bytes, 1, f) == 1, "short handle file");
   std::fclose(f);
-  return reinterpret_cast<sxt_multiexp_handle*>(h);
+  return reinterpret_cast<sxt_multiexp_handle*>(handle_new(curve_id, host.data(), hdr[3]));
 }
 
 void sxt_fixed_multiexponentiation(void* res, const struct sxt_multiexp_handle* handle,
@@ -375,11 +383,7 @@ void sxt_fixed_multiexponentiation(void* res, const struct sxt_multiexp_handle* 
   require_init("sxt_fixed_multiexponentiation");
   const Handle* h = reinterpret_cast<const Handle*>(handle);
   B200_REQUIRE(h != nullptr, "null handle");
-  dispatch(h->curve_id, [&](auto c) {
-    fixed_host<decltype(c)>(res, h, 0, element_num_bytes, nullptr, nullptr, num_outputs, n,
-                            scalars);
-    return 0;
-  });
+  fixed_host(res, h, 0, element_num_bytes, nullptr, nullptr, num_outputs, n, scalars);
 }
 void sxt_fixed_packed_multiexponentiation(void* res, const struct sxt_multiexp_handle* handle,
                                           const unsigned* output_bit_table, unsigned num_outputs,
@@ -388,10 +392,7 @@ void sxt_fixed_packed_multiexponentiation(void* res, const struct sxt_multiexp_h
   require_init("sxt_fixed_packed_multiexponentiation");
   const Handle* h = reinterpret_cast<const Handle*>(handle);
   B200_REQUIRE(h != nullptr, "null handle");
-  dispatch(h->curve_id, [&](auto c) {
-    fixed_host<decltype(c)>(res, h, 1, 0, output_bit_table, nullptr, num_outputs, n, scalars);
-    return 0;
-  });
+  fixed_host(res, h, 1, 0, output_bit_table, nullptr, num_outputs, n, scalars);
 }
 void sxt_fixed_vlen_multiexponentiation(void* res, const struct sxt_multiexp_handle* handle,
                                         const unsigned* output_bit_table,
@@ -401,11 +402,7 @@ void sxt_fixed_vlen_multiexponentiation(void* res, const struct sxt_multiexp_han
   require_init("sxt_fixed_vlen_multiexponentiation");
   const Handle* h = reinterpret_cast<const Handle*>(handle);
   B200_REQUIRE(h != nullptr, "null handle");
-  dispatch(h->curve_id, [&](auto c) {
-    fixed_host<decltype(c)>(res, h, 2, 0, output_bit_table, output_lengths, num_outputs, 0,
-                            scalars);
-    return 0;
-  });
+  fixed_host(res, h, 2, 0, output_bit_table, output_lengths, num_outputs, 0, scalars);
 }
 
 // =====================================================================================================
@@ -417,9 +414,7 @@ void b200_set_device(int device) {
   g_state.device = device;
 }
 unsigned long long b200_launch_count(void) { return LaunchCounter::value(); }
-unsigned b200_point_bytes(unsigned curve_id) {
-  return dispatch(curve_id, [](auto c) { return (unsigned)sizeof(typename decltype(c)::Point); });
-}
+unsigned b200_point_bytes(unsigned curve_id) { return vt(curve_id).point_bytes; }
 void* b200_malloc(uint64_t bytes) {
   std::lock_guard<std::mutex> lock(g_mutex);
   require_init("b200_malloc");
@@ -477,38 +472,27 @@ void b200_commit_device(unsigned curve_id, void* out_commitments, void* out_part
     return;
   std::lock_guard<std::mutex> lock(g_mutex);
   require_init("b200_commit_device");
-  dispatch(curve_id, [&](auto c) {
-    CurveOps<decltype(c)>::commit_device(ctx(), out_commitments, out_partials, num_sequences,
-                                         descriptors, generators, offset_generators);
-    return 0;
-  });
+  vt(curve_id).commit_device(ctx(), out_commitments, out_partials, num_sequences, descriptors,
+                             generators, offset_generators);
 }
 void b200_combine_partials_device(unsigned curve_id, void* out_commitments, const void* partials,
                                   uint32_t num_parts, uint32_t count) {
   std::lock_guard<std::mutex> lock(g_mutex);
   require_init("b200_combine_partials_device");
-  cudaStream_t s = g_state.stream;
-  dispatch(curve_id, [&](auto c) {
-    typedef decltype(c) C;
-    DevBuf<typename C::Point> sum(count, s);
-    CurveOps<C>::sum_parts(ctx(), partials, num_parts, count, sum.p);
-    CurveOps<C>::store(ctx(), sum.p, out_commitments, count, true);
-    return 0;
-  });
+  const CurveVTable& V = vt(curve_id);
+  DevBuf<unsigned char> sum((size_t)count * V.point_bytes, g_state.stream);
+  V.sum_parts(ctx(), partials, num_parts, count, sum.p);
+  V.store(ctx(), sum.p, out_commitments, count, true);
 }
 void b200_combine_partials_projective_device(unsigned curve_id, void* out_res,
                                              const void* partials, uint32_t num_parts,
                                              uint32_t count) {
   std::lock_guard<std::mutex> lock(g_mutex);
   require_init("b200_combine_partials_projective_device");
-  cudaStream_t s = g_state.stream;
-  dispatch(curve_id, [&](auto c) {
-    typedef decltype(c) C;
-    DevBuf<typename C::Point> sum(count, s);
-    CurveOps<C>::sum_parts(ctx(), partials, num_parts, count, sum.p);
-    CurveOps<C>::store(ctx(), sum.p, out_res, count, false);
-    return 0;
-  });
+  const CurveVTable& V = vt(curve_id);
+  DevBuf<unsigned char> sum((size_t)count * V.point_bytes, g_state.stream);
+  V.sum_parts(ctx(), partials, num_parts, count, sum.p);
+  V.store(ctx(), sum.p, out_res, count, false);
 }
 void b200_fixed_msm_device(void* out_res, void* out_partials,
                            const struct sxt_multiexp_handle* handle, int mode,
@@ -527,12 +511,8 @@ void b200_fixed_msm_device(void* out_res, void* out_partials,
     for (unsigned j = 0; j < num_outputs; ++j)
       rows = output_lengths[j] > rows ? output_lengths[j] : rows;
   }
-  dispatch(h->curve_id, [&](auto c) {
-    CurveOps<decltype(c)>::fixed_device(ctx(), out_res, out_partials, h, mode,
-                                        element_num_bytes, output_bit_table, output_lengths,
-                                        num_outputs, rows, scalars);
-    return 0;
-  });
+  vt(h->curve_id).fixed_device(ctx(), out_res, out_partials, h, mode, element_num_bytes,
+                               output_bit_table, output_lengths, num_outputs, rows, scalars);
 }
 void b200_set_reduce_groups(unsigned g1, unsigned gn) {
   std::lock_guard<std::mutex> lock(g_mutex);

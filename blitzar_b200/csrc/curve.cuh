@@ -63,7 +63,7 @@ struct QuadExec {
       x.l[k] = lane == 0 ? a0.l[k] : (lane == 1 ? a1.l[k] : (lane == 2 ? a2.l[k] : a3.l[k]));
       y.l[k] = lane == 0 ? b0.l[k] : (lane == 1 ? b1.l[k] : (lane == 2 ? b2.l[k] : b3.l[k]));
     }
-    F::mul(r, x, y);
+    F::mul_lat(r, x, y);
 #pragma unroll
     for (int k = 0; k < F::N; ++k) {
       o0.l[k] = __shfl_sync(mask, r.l[k], 0, 4);
@@ -88,7 +88,7 @@ struct QuadExec {
       x.l[k] = lane ? a1.l[k] : a0.l[k];
       y.l[k] = lane ? b1.l[k] : b0.l[k];
     }
-    F::mul(r, x, y);
+    F::mul_lat(r, x, y);
 #pragma unroll
     for (int k = 0; k < F::N; ++k) {
       o0.l[k] = __shfl_sync(mask, r.l[k], 0, 4);

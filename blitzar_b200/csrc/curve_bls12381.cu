@@ -1,6 +1,6 @@
 // Instantiates every kernel of the MSM engine for Bls12381G1 (one translation unit per curve so the
-// four curves compile in parallel).
+// four curves compile in parallel) and exports them through the curve's vtable.
 #include "engine.cuh"
 namespace b200 {
-template struct CurveOps<Bls12381G1>;
+B200_DEFINE_CURVE_VTABLE(kVTableBls12381, Bls12381G1);
 }  // namespace b200

@@ -1,6 +1,6 @@
 // Instantiates every kernel of the MSM engine for Bn254G1 (one translation unit per curve so the
-// four curves compile in parallel).
+// four curves compile in parallel) and exports them through the curve's vtable.
 #include "engine.cuh"
 namespace b200 {
-template struct CurveOps<Bn254G1>;
+B200_DEFINE_CURVE_VTABLE(kVTableBn254, Bn254G1);
 }  // namespace b200

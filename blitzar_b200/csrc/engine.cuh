@@ -5,33 +5,10 @@
 #include <cstdint>
 #include <vector>
 
-#include "../../include/blitzar_b200.h"
+#include "engine_api.cuh"
 #include "msm.cuh"
 
 namespace b200 {
-
-struct EngineCtx {
-  stream_t s;
-  MsmOptions opt;
-  const Ed25519::Gen* builtin;  // device-resident built-in generators g(0..num_builtin)
-  uint64_t num_builtin;
-};
-
-template <class T> struct DevBuf {
-  T* p = nullptr;
-  stream_t s;
-  DevBuf(size_t count, stream_t s_) : s(s_) { p = (T*)dev_alloc(count * sizeof(T), s); }
-  ~DevBuf() { dev_free(p, s); }
-  DevBuf(const DevBuf&) = delete;
-  DevBuf& operator=(const DevBuf&) = delete;
-};
-
-// ---- per-curve glue --------------------------------------------------------------------------------
-struct Handle {
-  unsigned curve_id;
-  unsigned n;
-  void* gens;  // device array of C::Gen
-};
 
 // validates like cbindings/pedersen.cc:44-68 and returns the longest column
 inline uint64_t check_descriptors(const sxt_sequence_descriptor* d, uint32_t num) {
@@ -93,7 +70,7 @@ template <class C> struct CurveOps {
       } else {
         if constexpr (C::kCurveId == kRistretto255) {
           if (offset_generators + n <= ctx.num_builtin)
-            gens_ptr = ctx.builtin + offset_generators;
+            gens_ptr = (const Gen*)ctx.builtin + offset_generators;
           else
             launch(BuiltinGeneratorBody{gens.p, offset_generators}, n, s);
         } else {
@@ -183,15 +160,18 @@ template <class C> struct CurveOps {
   }
 };
 
-// built-in ristretto generators g(first .. first+n) into the device generator layout
-void launch_builtin_generators(const EngineCtx& ctx, Ed25519::Gen* gens, uint64_t first,
-                               uint64_t n);
-
-#ifdef B200_EXTERN_CURVES
-extern template struct CurveOps<Ed25519>;
-extern template struct CurveOps<Bls12381G1>;
-extern template struct CurveOps<Bn254G1>;
-extern template struct CurveOps<GrumpkinG>;
-#endif
+#define B200_DEFINE_CURVE_VTABLE(NAME, C)                                                          \
+  const CurveVTable NAME = {C::kCurveId,                                                           \
+                            (unsigned)sizeof(typename C::Point),                                   \
+                            (unsigned)sizeof(typename C::Gen),                                     \
+                            (unsigned)C::kAbiGenBytes,                                             \
+                            (unsigned)C::kAbiProjBytes,                                            \
+                            (unsigned)C::kAbiCommitBytes,                                          \
+                            &CurveOps<C>::commit_device,                                           \
+                            &CurveOps<C>::fixed_device,                                            \
+                            &CurveOps<C>::ingest_projective,                                       \
+                            &CurveOps<C>::gens_to_projective,                                      \
+                            &CurveOps<C>::store,                                                   \
+                            &CurveOps<C>::sum_parts}
 
 }  // namespace b200

@@ -281,6 +281,46 @@ struct F25519 {
   }
   static B200_HD void sqr(E& r, const E& a) { mul(r, a, a); }
 
+  // latency-oriented schedule for the serial tail kernels (QuadExec): product scanning — the 15
+  // column sums are independent 96-bit accumulations, so one warp can overlap them; more
+  // instructions than mul() but a much shorter dependent chain.
+  static B200_HD void mul_lat(E& r, const E& a, const E& b) {
+    u64 lo[16];
+    u32 hi[16];
+#pragma unroll
+    for (int k = 0; k < 15; ++k) {
+      u64 acc = 0;
+      u32 c = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int j = k - i;
+        if (j >= 0 && j < 8) {
+          u64 p = (u64)a.l[i] * b.l[j];
+          acc += p;
+          c += acc < p ? 1u : 0u;
+        }
+      }
+      lo[k] = acc;
+      hi[k] = c;
+    }
+    // column k contributes lo32 to limb k, hi32 to limb k+1 and its overflow count to limb k+2
+    u32 t[16];
+    u64 carry = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      u64 v = carry;
+      if (k < 15)
+        v += (u32)lo[k];
+      if (k >= 1)
+        v += (u32)(lo[k - 1] >> 32);
+      if (k >= 2)
+        v += hi[k - 2];
+      t[k] = (u32)v;
+      carry = v >> 32;
+    }
+    fold(r, t);
+  }
+
   static B200_HD void fold(E& r, const u32* t) {
     u64 c = 0;
 #pragma unroll
@@ -611,6 +651,7 @@ template <class P> struct Mont {
     for (int i = 0; i < N; ++i)
       r.l[i] = bw ? s.l[i] : d.l[i];
   }
+  static B200_HD void mul_lat(E& r, const E& a, const E& b) { mul(r, a, b); }
   // reference schedule (plain 64-bit C): CIOS Montgomery product r = a*b/R mod p
   static B200_HD void mul_ref(E& r, const E& a, const E& b) {
     u32 t[N + 2];

@@ -21,7 +21,7 @@
 #include <vector>
 
 #include "curve.cuh"
-#include "runtime.cuh"
+#include "engine_api.cuh"
 
 namespace b200 {
 
@@ -504,15 +504,6 @@ inline u32 choose_window_bits(u64 max_n, u32 max_width) {
   }
   return best;
 }
-
-struct MsmOptions {
-  u32 window_bits = 0;  // 0 = choose from n
-  u32 chunk1 = 32;      // chunk length of the first accumulation level
-  u32 chunkn = 8;       // chunk length of the cascade levels
-  u32 reduce_g1 = 8;    // bucket-reduction group size, first level (power of two)
-  u32 reduce_gn = 8;    // bucket-reduction group size, later levels (power of two)
-  u64 quad_threshold = 32768;  // launches with at most this many logical threads run 4 lanes each
-};
 
 // Computes out[j] = sum_i scalar(j,i) * G_i for every column j. `cols` are host descriptors whose
 // `base` pointers are DEVICE pointers; gens and out are device arrays. first_window/num_windows

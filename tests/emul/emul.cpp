@@ -111,6 +111,9 @@ extern "C" int emul_check_mul(unsigned field_id, unsigned iters, unsigned seed) 
       F25519::canonical(c1, r1);
       F25519::canonical(c2, r2);
       for (int i = 0; i < 8; ++i) if (c1.l[i] != c2.l[i]) { ++bad; break; }
+      F25519::mul_lat(r1, a, b);
+      F25519::canonical(c1, r1);
+      for (int i = 0; i < 8; ++i) if (c1.l[i] != c2.l[i]) { ++bad; break; }
     }
     return bad;
   }
