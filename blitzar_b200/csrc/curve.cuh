@@ -46,7 +46,10 @@ struct SeqExec {
     F::mul(o1, a1, b1);
   }
 };
-struct QuadExec {
+// kFullMask = true: shuffles name the whole warp (fast path; every non-exited lane of the warp must
+// reach the call convergently). kFullMask = false: shuffles name only the quad (safe when quads of
+// one warp diverge, but a run-time partial mask costs tens of cycles per shuffle).
+template <bool kFullMask> struct QuadExecT {
   static constexpr int kLanes = 4;
   template <class F>
   static B200_HD void mul4(typename F::E& o0, typename F::E& o1, typename F::E& o2,
@@ -56,14 +59,17 @@ struct QuadExec {
                            const typename F::E& a3, const typename F::E& b3) {
 #ifdef __CUDA_ARCH__
     const unsigned lane = threadIdx.x & 3u;
-    const unsigned mask = 0xFu << (threadIdx.x & 28u);
+    const unsigned mask = kFullMask ? 0xffffffffu : (0xFu << (threadIdx.x & 28u));
     typename F::E x, y, r;
+    // mask-and-or operand selection: guaranteed branch-free (ternaries compile to divergent code)
+    const u32 m0 = lane == 0 ? ~0u : 0u, m1 = lane == 1 ? ~0u : 0u, m2 = lane == 2 ? ~0u : 0u,
+              m3 = lane == 3 ? ~0u : 0u;
 #pragma unroll
     for (int k = 0; k < F::N; ++k) {
-      x.l[k] = lane == 0 ? a0.l[k] : (lane == 1 ? a1.l[k] : (lane == 2 ? a2.l[k] : a3.l[k]));
-      y.l[k] = lane == 0 ? b0.l[k] : (lane == 1 ? b1.l[k] : (lane == 2 ? b2.l[k] : b3.l[k]));
+      x.l[k] = (a0.l[k] & m0) | (a1.l[k] & m1) | (a2.l[k] & m2) | (a3.l[k] & m3);
+      y.l[k] = (b0.l[k] & m0) | (b1.l[k] & m1) | (b2.l[k] & m2) | (b3.l[k] & m3);
     }
-    F::mul_lat(r, x, y);
+    F::mul(r, x, y);
 #pragma unroll
     for (int k = 0; k < F::N; ++k) {
       o0.l[k] = __shfl_sync(mask, r.l[k], 0, 4);
@@ -81,14 +87,15 @@ struct QuadExec {
                            const typename F::E& b1) {
 #ifdef __CUDA_ARCH__
     const unsigned lane = threadIdx.x & 1u;
-    const unsigned mask = 0xFu << (threadIdx.x & 28u);
+    const unsigned mask = kFullMask ? 0xffffffffu : (0xFu << (threadIdx.x & 28u));
     typename F::E x, y, r;
+    const u32 m1 = lane ? ~0u : 0u, m0 = ~m1;
 #pragma unroll
     for (int k = 0; k < F::N; ++k) {
-      x.l[k] = lane ? a1.l[k] : a0.l[k];
-      y.l[k] = lane ? b1.l[k] : b0.l[k];
+      x.l[k] = (a0.l[k] & m0) | (a1.l[k] & m1);
+      y.l[k] = (b0.l[k] & m0) | (b1.l[k] & m1);
     }
-    F::mul_lat(r, x, y);
+    F::mul(r, x, y);
 #pragma unroll
     for (int k = 0; k < F::N; ++k) {
       o0.l[k] = __shfl_sync(mask, r.l[k], 0, 4);
@@ -99,6 +106,8 @@ struct QuadExec {
 #endif
   }
 };
+typedef QuadExecT<false> QuadExec;
+typedef QuadExecT<true> QuadExecConv;
 
 // ================================================================================================
 // ed25519 / ristretto255

@@ -646,8 +646,8 @@ void msm_run(stream_t s, const typename C::Gen* gens, std::vector<ColumnDesc> co
       u32 m_out = m / g;
       Point* Xout = (Point*)dev_alloc((u64)total_windows * m_out * sizeof(Point), s);
       Point* Cout = (Point*)dev_alloc((u64)total_windows * m_out * sizeof(Point), s);
-      if ((u64)total_windows * m_out <= opt.quad_threshold)
-        launch(ReduceBody<C, QuadExec>{X, Cin, m, g, log2g, Xout, Cout, d_counts, nbuckets},
+      if ((u64)total_windows * m_out <= opt.quad_threshold)  // uniform control flow: full-warp shuffles
+        launch(ReduceBody<C, QuadExecConv>{X, Cin, m, g, log2g, Xout, Cout, d_counts, nbuckets},
                (u64)total_windows * m_out * QuadExec::kLanes, s);
       else
         launch(ReduceBody<C>{X, Cin, m, g, log2g, Xout, Cout, d_counts, nbuckets},
@@ -665,7 +665,12 @@ void msm_run(stream_t s, const typename C::Gen* gens, std::vector<ColumnDesc> co
     for (void* p : to_free)
       dev_free(p, s);
   }
-  if (ncols <= opt.quad_threshold)
+  bool uniform_windows = true;  // same Horner trip count in every quad of a warp
+  for (u32 j = 1; j < ncols; ++j)
+    uniform_windows = uniform_windows && cols[j].num_windows == cols[0].num_windows;
+  if (ncols <= opt.quad_threshold && uniform_windows)
+    launch(CombineBody<C, QuadExecConv>{d_S, d_cols, c, out}, (u64)ncols * QuadExec::kLanes, s);
+  else if (ncols <= opt.quad_threshold)
     launch(CombineBody<C, QuadExec>{d_S, d_cols, c, out}, (u64)ncols * QuadExec::kLanes, s);
   else
     launch(CombineBody<C>{d_S, d_cols, c, out}, ncols, s);
