@@ -5,6 +5,7 @@
 //
 // Replaces: cbindings/{backend,pedersen,fixed_pedersen,get_generators,get_one_commit}.cc and the
 // gpu_backend methods they dispatch to (sxt/cbindings/backend/gpu_backend.cc:150-334).
+#include <algorithm>
 #include <cctype>
 #include <cstdint>
 #include <cstdio>
@@ -23,7 +24,10 @@ namespace {
 struct State {
   bool initialized = false;
   int device = -1;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;       // every kernel of the engine
+  cudaStream_t copy_stream = nullptr;  // host-to-device staging of the C-ABI calls
+  cudaEvent_t range_events[16] = {};
+  cudaEvent_t alloc_event = nullptr;
   void* builtin = nullptr;  // g(0..num_builtin) device-resident, ed25519 generator layout
   uint64_t num_builtin = 0;
   MsmOptions opt;
@@ -48,6 +52,10 @@ void ensure_device() {
   }
   B200_CUDA(cudaSetDevice(g_state.device));
   B200_CUDA(cudaStreamCreateWithFlags(&g_state.stream, cudaStreamNonBlocking));
+  B200_CUDA(cudaStreamCreateWithFlags(&g_state.copy_stream, cudaStreamNonBlocking));
+  for (auto& e : g_state.range_events)
+    B200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  B200_CUDA(cudaEventCreateWithFlags(&g_state.alloc_event, cudaEventDisableTiming));
   cudaMemPool_t pool;
   B200_CUDA(cudaDeviceGetDefaultMemPool(&pool, g_state.device));
   uint64_t threshold = UINT64_MAX;  // keep freed blocks cached in the pool between calls
@@ -90,7 +98,24 @@ uint64_t longest_column(const sxt_sequence_descriptor* d, uint32_t num) {
   return longest;
 }
 
-// host-pointer commitments: H2D, device MSM, D2H
+// Host-pointer commitments. The generator range is split into pieces; the copy stream uploads piece
+// after piece (scalars rows + generators) while the compute stream sorts and accumulates the
+// previous one into the shared bucket array, so most of the PCIe time hides behind the kernels.
+struct RangeWaitState {
+  uint64_t n;
+  uint32_t num_ranges;
+};
+void wait_for_range(void* user, uint64_t begin, uint64_t) {
+  auto* st = static_cast<RangeWaitState*>(user);
+  for (uint32_t r = 0; r < st->num_ranges; ++r)
+    if (range_begin(st->n, r, st->num_ranges) == begin) {
+      B200_CUDA(cudaStreamWaitEvent(g_state.stream, g_state.range_events[r], 0));
+      return;
+    }
+  // a range the copy schedule does not know (column groups): wait for everything
+  B200_CUDA(cudaStreamWaitEvent(g_state.stream, g_state.range_events[st->num_ranges - 1], 0));
+}
+
 void commit_host(unsigned curve_id, void* commitments, uint32_t num,
                  const sxt_sequence_descriptor* d, const void* generators,
                  uint64_t offset_generators, const char* fn) {
@@ -100,7 +125,7 @@ void commit_host(unsigned curve_id, void* commitments, uint32_t num,
   require_init(fn);
   B200_REQUIRE(commitments != nullptr, "commitments == nullptr");
   const CurveVTable& V = vt(curve_id);
-  cudaStream_t s = g_state.stream;
+  cudaStream_t s = g_state.stream, sc = g_state.copy_stream;
   uint64_t n = longest_column(d, num);
   if (curve_id != SXT_CURVE_RISTRETTO255)
     B200_REQUIRE(generators != nullptr, "generators == nullptr");
@@ -111,17 +136,36 @@ void commit_host(unsigned curve_id, void* commitments, uint32_t num,
   DevBuf<unsigned char> scal(total_scalar_bytes, s);
   DevBuf<unsigned char> out((size_t)num * V.abi_commit_bytes, s);
   std::vector<sxt_sequence_descriptor> dd(d, d + num);
+  std::vector<size_t> col_off(num);
   size_t off = 0;
   for (uint32_t i = 0; i < num; ++i) {
-    size_t bytes = (size_t)d[i].n * d[i].element_nbytes;
-    copy_h2d(scal.p + off, d[i].data, bytes, s);
+    col_off[i] = off;
     dd[i].data = scal.p + off;
-    off += (bytes + 31) & ~(size_t)31;
+    off += ((size_t)d[i].n * d[i].element_nbytes + 31) & ~(size_t)31;
   }
-  if (generators)
-    copy_h2d(raw_gens.p, generators, n * V.abi_gen_bytes, s);
+  // pieces of >= 2^18 terms, at most 8; many columns make the kernels dominate, so one piece
+  uint32_t num_ranges = 1;
+  if (n >= (1ull << 19) && num <= 4)
+    num_ranges = (uint32_t)std::min<uint64_t>(8, n >> 18);
+  // the destination buffers are stream-ordered allocations of the compute stream
+  B200_CUDA(cudaEventRecord(g_state.alloc_event, s));
+  B200_CUDA(cudaStreamWaitEvent(sc, g_state.alloc_event, 0));
+  for (uint32_t r = 0; r < num_ranges; ++r) {
+    const uint64_t b = range_begin(n, r, num_ranges), e = range_begin(n, r + 1, num_ranges);
+    for (uint32_t i = 0; i < num; ++i) {
+      const uint64_t lo = std::min<uint64_t>(b, d[i].n), hi = std::min<uint64_t>(e, d[i].n);
+      copy_h2d(scal.p + col_off[i] + lo * d[i].element_nbytes,
+               d[i].data + lo * d[i].element_nbytes, (hi - lo) * d[i].element_nbytes, sc);
+    }
+    if (generators)
+      copy_h2d(raw_gens.p + b * V.abi_gen_bytes,
+               static_cast<const unsigned char*>(generators) + b * V.abi_gen_bytes,
+               (e - b) * V.abi_gen_bytes, sc);
+    B200_CUDA(cudaEventRecord(g_state.range_events[r], sc));
+  }
+  RangeWaitState st{n, num_ranges};
   V.commit_device(ctx(), out.p, nullptr, num, dd.data(), generators ? raw_gens.p : nullptr,
-                  offset_generators);
+                  offset_generators, num_ranges, &wait_for_range, &st);
   copy_d2h(commitments, out.p, (size_t)num * V.abi_commit_bytes, s);
   stream_sync(s);
 }
@@ -285,7 +329,7 @@ int sxt_curve25519_get_one_commit(struct sxt_ristretto255* one_commit, uint64_t 
   sxt_sequence_descriptor d{1, n, ones.p, 0};
   DevBuf<unsigned char> pt(V.point_bytes, s);
   DevBuf<unsigned char> out(V.abi_proj_bytes, s);
-  V.commit_device(ctx(), nullptr, pt.p, 1, &d, nullptr, 0);
+  V.commit_device(ctx(), nullptr, pt.p, 1, &d, nullptr, 0, 1, nullptr, nullptr);
   V.store(ctx(), pt.p, out.p, 1, false);
   copy_d2h(one_commit, out.p, V.abi_proj_bytes, s);
   stream_sync(s);
@@ -473,7 +517,7 @@ void b200_commit_device(unsigned curve_id, void* out_commitments, void* out_part
   std::lock_guard<std::mutex> lock(g_mutex);
   require_init("b200_commit_device");
   vt(curve_id).commit_device(ctx(), out_commitments, out_partials, num_sequences, descriptors,
-                             generators, offset_generators);
+                             generators, offset_generators, 1, nullptr, nullptr);
 }
 void b200_combine_partials_device(unsigned curve_id, void* out_commitments, const void* partials,
                                   uint32_t num_parts, uint32_t count) {
@@ -524,8 +568,8 @@ void b200_set_reduce_groups(unsigned g1, unsigned gn) {
       p *= 2;
     return p;
   };
-  g_state.opt.reduce_g1 = pow2(g1, 8u);
-  g_state.opt.reduce_gn = pow2(gn, 8u);
+  g_state.opt.reduce_g1 = pow2(g1, 16u);
+  g_state.opt.reduce_gn = pow2(gn, 4u);
 }
 void b200_profile_accumulate(int enable) {
   std::lock_guard<std::mutex> lock(g_mutex);

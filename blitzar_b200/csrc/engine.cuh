@@ -37,7 +37,7 @@ template <class C> struct CurveOps {
   // Columns are processed in groups so that (terms x windows) stays below 2^32 entries and the
   // sort scratch stays within a few GB of HBM.
   static void run_columns(const EngineCtx& ctx, const Gen* gens, std::vector<ColumnDesc>& cols,
-                          Point* out) {
+                          Point* out, u32 num_ranges = 1, RangeHook* hook = nullptr) {
     const uint64_t kMaxEntries = 1ull << 30;
     size_t b = 0;
     while (b < cols.size()) {
@@ -51,32 +51,73 @@ template <class C> struct CurveOps {
         ++e;
       }
       std::vector<ColumnDesc> group(cols.begin() + b, cols.begin() + e);
-      msm_run<C>(ctx.s, gens, group, out + b, ctx.opt);
+      const bool whole = b == 0 && e == cols.size();
+      // range hooks assume one pass over the generators; several column groups each see all of them
+      if (!whole && hook && b == 0)
+        hook->before_range(0, ~0ull);
+      msm_run<C>(ctx.s, gens, group, out + b, ctx.opt, whole ? num_ranges : 1,
+                 whole ? hook : nullptr);
       b = e;
     }
   }
 
-  // device-resident variable-base MSM; descriptors[i].data and generators_dev are device pointers
+  // generator ingestion of one range: ABI layout (device) -> device generator layout
+  struct IngestHook : RangeHook {
+    const EngineCtx* ctx;
+    const unsigned char* raw;  // ABI-layout generators on the device, or null
+    Gen* gens;
+    uint64_t n, offset_generators;
+    bool builtin;  // generate g(offset + i) instead of converting `raw`
+    range_wait_fn wait;
+    void* wait_user;
+    void before_range(u64 begin, u64 end) override {
+      if (end > n)
+        end = n;
+      if (begin >= end)
+        return;
+      if (wait)
+        wait(wait_user, begin, end);
+      if (raw)
+        launch(IngestBody<C, false>{raw + begin * C::kAbiGenBytes, gens + begin}, end - begin,
+               ctx->s);
+      else if (builtin)
+        launch_builtin(ctx->s, gens + begin, offset_generators + begin, end - begin);
+    }
+  };
+  static void launch_builtin(stream_t s, Gen* gens, uint64_t first, uint64_t count) {
+    if constexpr (C::kCurveId == kRistretto255)
+      launch(BuiltinGeneratorBody{gens, first}, count, s);
+    else
+      die("generators == nullptr", __FILE__, __LINE__);
+  }
+
+  // device-resident variable-base MSM; descriptors[i].data and generators_dev are device pointers.
+  // The generator range is processed in num_ranges pieces; `wait` (optional) is called on the host
+  // before each piece is touched.
   static void commit_device(const EngineCtx& ctx, void* out_commitments, void* out_partials,
                             uint32_t num, const sxt_sequence_descriptor* d,
-                            const void* generators_dev, uint64_t offset_generators) {
+                            const void* generators_dev, uint64_t offset_generators,
+                            uint32_t num_ranges, range_wait_fn wait, void* wait_user) {
     stream_t s = ctx.s;
     uint64_t n = check_descriptors(d, num);
     DevBuf<Gen> gens(n ? n : 1, s);
     const Gen* gens_ptr = gens.p;
-    if (n) {
-      if (generators_dev) {
-        launch(IngestBody<C, false>{(const unsigned char*)generators_dev, gens.p}, n, s);
-      } else {
-        if constexpr (C::kCurveId == kRistretto255) {
-          if (offset_generators + n <= ctx.num_builtin)
-            gens_ptr = (const Gen*)ctx.builtin + offset_generators;
-          else
-            launch(BuiltinGeneratorBody{gens.p, offset_generators}, n, s);
-        } else {
-          die("generators == nullptr", __FILE__, __LINE__);
-        }
-      }
+    IngestHook hook;
+    hook.ctx = &ctx;
+    hook.raw = (const unsigned char*)generators_dev;
+    hook.gens = gens.p;
+    hook.n = n;
+    hook.offset_generators = offset_generators;
+    hook.builtin = false;
+    hook.wait = wait;
+    hook.wait_user = wait_user;
+    if (n && !generators_dev) {
+      if (C::kCurveId != kRistretto255)
+        die("generators == nullptr", __FILE__, __LINE__);
+      if (offset_generators + n <= ctx.num_builtin)
+        gens_ptr = (const Gen*)ctx.builtin + offset_generators;
+      else
+        hook.builtin = true;
     }
     std::vector<ColumnDesc> cols(num);
     for (uint32_t i = 0; i < num; ++i) {
@@ -92,7 +133,7 @@ template <class C> struct CurveOps {
     DevBuf<Point> tmp(out_partials ? 1 : num, s);
     if (!pts)
       pts = tmp.p;
-    run_columns(ctx, gens_ptr, cols, pts);
+    run_columns(ctx, gens_ptr, cols, pts, num_ranges ? num_ranges : 1, &hook);
     if (out_commitments)
       launch(StoreBody<C, true>{pts, (unsigned char*)out_commitments}, num, s);
   }

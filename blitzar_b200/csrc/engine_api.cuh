@@ -12,8 +12,8 @@ struct MsmOptions {
   u32 window_bits = 0;  // 0 = choose from n
   u32 chunk1 = 32;      // chunk length of the first accumulation level
   u32 chunkn = 8;       // chunk length of the cascade levels
-  u32 reduce_g1 = 8;    // bucket-reduction group size, first level (power of two)
-  u32 reduce_gn = 8;    // bucket-reduction group size, later levels (power of two)
+  u32 reduce_g1 = 16;   // bucket-reduction group size, first level (power of two)
+  u32 reduce_gn = 4;    // bucket-reduction group size, later levels (power of two)
   u64 quad_threshold = 32768;  // launches with at most this many logical threads run 4 lanes each
 };
 
@@ -39,11 +39,21 @@ template <class T> struct DevBuf {
   DevBuf& operator=(const DevBuf&) = delete;
 };
 
+// generator-range r of `num_ranges` over n terms starts here (shared by the engine and the C-ABI
+// layer, which schedules the host-to-device copies of each range)
+inline uint64_t range_begin(uint64_t n, uint32_t r, uint32_t num_ranges) {
+  return n * r / num_ranges;
+}
+// called on the host before the engine touches terms [begin, end) (e.g. make the compute stream wait
+// for that range's copies)
+typedef void (*range_wait_fn)(void* user, uint64_t begin, uint64_t end);
+
 struct CurveVTable {
   unsigned curve_id, point_bytes, gen_bytes, abi_gen_bytes, abi_proj_bytes, abi_commit_bytes;
   void (*commit_device)(const EngineCtx&, void* out_commitments, void* out_partials, uint32_t num,
                         const sxt_sequence_descriptor* d, const void* generators_dev,
-                        uint64_t offset_generators);
+                        uint64_t offset_generators, uint32_t num_ranges, range_wait_fn wait,
+                        void* wait_user);
   void (*fixed_device)(const EngineCtx&, void* out_res, void* out_partials, const Handle* h,
                        int mode, unsigned element_num_bytes, const unsigned* bit_table,
                        const unsigned* lengths, unsigned num_outputs, unsigned n,

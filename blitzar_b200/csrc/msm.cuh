@@ -276,11 +276,23 @@ template <class C, bool kGather, class X = SeqExec> struct AccumulateBody {
   const u32* m_ptr;                // number of entries at this level (device)
   u32 K;
   u32 final_level;
+  u32 add_into;                    // buckets already hold earlier generator chunks: add, don't store
   Point* buckets;
   u32* out_keys;
   Point* out_pieces;
   u32* out_m_ptr;
 
+  // every lane of a quad takes part in the addition; only the writer lane stores
+  B200_HD void put_bucket_guarded(u32 key, const Point& acc, bool writer) const {
+    if (add_into) {
+      Point b = buckets[key];
+      C::template add<X>(b, b, acc);
+      if (writer)
+        buckets[key] = b;
+    } else if (writer) {
+      buckets[key] = acc;
+    }
+  }
   B200_HD u32 key_at(u64 i) const { return kGather ? (u32)(entries[i] >> 32) : keys[i]; }
   B200_HD void fetch(Point& acc, u64 i, bool first) const {
     if (kGather) {
@@ -316,10 +328,10 @@ template <class C, bool kGather, class X = SeqExec> struct AccumulateBody {
       if (k == cur) {
         fetch(acc, i, false);
       } else {
-        if (writer) {
-          if (final_level || !first_seg) {
-            buckets[cur] = acc;
-          } else {
+        if (final_level || !first_seg) {
+          put_bucket_guarded(cur, acc, writer);
+        } else if (writer) {
+          {
             out_keys[2 * t] = cur;
             out_pieces[2 * t] = acc;
           }
@@ -329,11 +341,13 @@ template <class C, bool kGather, class X = SeqExec> struct AccumulateBody {
         fetch(acc, i, true);
       }
     }
+    if (final_level) {
+      put_bucket_guarded(cur, acc, writer);
+      return;
+    }
     if (!writer)
       return;
-    if (final_level) {
-      buckets[cur] = acc;
-    } else if (first_seg) {  // single-segment chunk: pad the tail slot with the identity
+    if (first_seg) {  // single-segment chunk: pad the tail slot with the identity
       out_keys[2 * t] = cur;
       out_pieces[2 * t] = acc;
       out_keys[2 * t + 1] = cur;
@@ -342,6 +356,21 @@ template <class C, bool kGather, class X = SeqExec> struct AccumulateBody {
       out_keys[2 * t + 1] = cur;
       out_pieces[2 * t + 1] = acc;
     }
+  }
+};
+
+// window_used[w] |= (some entry of this pass landed in window w); bucket_end = cursor array after
+// the scatter (end offset of every bucket)
+struct WindowUsedBody {
+  static constexpr int kBlock = 64;
+  const u32* bucket_end;
+  u32 nbuckets;
+  u32* window_used;
+  B200_HD void operator()(u64 w) const {
+    u32 lo = w ? bucket_end[w * nbuckets - 1] : 0u;
+    u32 hi = bucket_end[(w + 1) * nbuckets - 1];
+    if (hi != lo)
+      window_used[w] = 1u;
   }
 };
 
@@ -357,7 +386,7 @@ template <class C, class Ex = SeqExec> struct ReduceBody {
   u32 m_in, g, log2g;
   Point* Xout;
   Point* Cout;
-  const u32* bucket_end;  // cursor array after the scatter: end offset of every bucket
+  const u32* window_used;  // per window: non-zero if any term was scattered into it
   u32 nbuckets;
   B200_HD void operator()(u64 tid) const {
     const u64 t = tid / Ex::kLanes;
@@ -365,9 +394,7 @@ template <class C, class Ex = SeqExec> struct ReduceBody {
     const u32 m_out = m_in / g;
     const u32 w = (u32)(t / m_out), k = (u32)(t % m_out);
     // empty window: nothing was scattered into any of its buckets
-    u32 lo = w ? bucket_end[(u64)w * nbuckets - 1] : 0u;
-    u32 hi = bucket_end[(u64)(w + 1) * nbuckets - 1];
-    if (lo == hi) {
+    if (window_used[w] == 0) {
       if (writer) {
         Xout[t] = C::identity();
         Cout[t] = C::identity();
@@ -505,181 +532,246 @@ inline u32 choose_window_bits(u64 max_n, u32 max_width) {
   return best;
 }
 
-// Computes out[j] = sum_i scalar(j,i) * G_i for every column j. `cols` are host descriptors whose
-// `base` pointers are DEVICE pointers; gens and out are device arrays. first_window/num_windows
-// are filled in here. Everything is enqueued on `s`; no host synchronisation.
-template <class C>
-void msm_run(stream_t s, const typename C::Gen* gens, std::vector<ColumnDesc> cols,
-             typename C::Point* out, const MsmOptions& opt = MsmOptions()) {
-  typedef typename C::Point Point;
-  const u32 ncols = (u32)cols.size();
-  if (ncols == 0)
-    return;
-  u64 max_n = 0, total_terms = 0;
+// Window / bucket geometry of one pass, fixed from the FULL columns so that generator-range chunks
+// of the same pass share one bucket array.
+struct MsmPlan {
+  u32 c = 0, nbuckets = 0, ncols = 0, total_windows = 0;
+  u64 nkeys = 0, max_n = 0, total_terms = 0;
+  std::vector<ColumnDesc> cols;  // first_window / num_windows filled in
+};
+
+inline MsmPlan msm_make_plan(std::vector<ColumnDesc> cols, const MsmOptions& opt) {
+  MsmPlan p;
+  p.ncols = (u32)cols.size();
   u32 max_width = 1;
   for (auto& col : cols) {
-    max_n = std::max<u64>(max_n, col.n);
+    p.max_n = std::max<u64>(p.max_n, col.n);
+    p.total_terms += col.n;
     if (col.n)
       max_width = std::max(max_width, col.bit_width);
   }
-  const u32 c = opt.window_bits ? opt.window_bits : choose_window_bits(max_n, max_width);
-  const u32 nbuckets = 1u << (c - 1);
+  p.c = opt.window_bits ? opt.window_bits : choose_window_bits(p.max_n, max_width);
+  p.nbuckets = 1u << (p.c - 1);
+  u64 max_entries = 0;
+  for (auto& col : cols) {
+    col.first_window = p.total_windows;
+    col.num_windows = col.n ? col.bit_width / p.c + 1 : 0;
+    p.total_windows += col.num_windows;
+    max_entries += (u64)col.n * col.num_windows;
+  }
+  p.nkeys = (u64)p.total_windows * p.nbuckets;
+  B200_REQUIRE(max_entries < (1ull << 32), "too many (term, window) entries for one pass");
+  B200_REQUIRE(p.nkeys < (1ull << 32), "too many buckets for one pass");
+  p.cols = std::move(cols);
+  return p;
+}
+
+// Sort + accumulate the terms [begin, end) of every column into d_buckets (indexed by the plan's
+// keys). gens[i] pairs with term i (absolute index). add_into: buckets already hold the sums of
+// earlier ranges. Enqueued on s.
+template <class C>
+void msm_accumulate_range(stream_t s, const MsmPlan& plan, const typename C::Gen* gens, u64 begin,
+                          u64 end, bool add_into, typename C::Point* d_buckets,
+                          u32* d_window_used, const MsmOptions& opt) {
+  typedef typename C::Point Point;
+  const u32 ncols = plan.ncols;
+  std::vector<ColumnDesc> cols(plan.cols);
   std::vector<u64> col_start(ncols + 1, 0);
-  u32 total_windows = 0;
   u64 max_entries = 0;
   for (u32 j = 0; j < ncols; ++j) {
-    cols[j].first_window = total_windows;
-    cols[j].num_windows = cols[j].n ? cols[j].bit_width / c + 1 : 0;
-    total_windows += cols[j].num_windows;
+    u64 lo = std::min<u64>(begin, cols[j].n), hi = std::min<u64>(end, cols[j].n);
+    cols[j].base += lo * cols[j].row_stride;
+    cols[j].n = (u32)(hi - lo);
     col_start[j + 1] = col_start[j] + cols[j].n;
     max_entries += (u64)cols[j].n * cols[j].num_windows;
   }
-  total_terms = col_start[ncols];
-  B200_REQUIRE(max_entries < (1ull << 32), "too many (term, window) entries for one pass");
-  B200_REQUIRE((u64)total_windows * nbuckets < (1ull << 32), "too many buckets for one pass");
-
-  ColumnDesc* d_cols = (ColumnDesc*)dev_alloc(ncols * sizeof(ColumnDesc), s);
-  copy_h2d(d_cols, cols.data(), ncols * sizeof(ColumnDesc), s);
-  if (total_terms == 0 || total_windows == 0) {
-    launch(FillIdentityBody<C>{out}, ncols, s);
-    dev_free(d_cols, s);
+  const u64 total_terms = col_start[ncols];
+  if (total_terms == 0)
     return;
-  }
-  u64* d_col_start = (u64*)dev_alloc((ncols + 1) * sizeof(u64), s);
-  copy_h2d(d_col_start, col_start.data(), (ncols + 1) * sizeof(u64), s);
-#ifndef B200_EMULATE
-  // the host vectors must outlive the async copies
-  stream_sync(s);
-#endif
+  const u32 c = plan.c, nbuckets = plan.nbuckets;
+  const u64 nkeys = plan.nkeys;
+  gens += begin;  // entry indices are relative to the range
 
-  const u64 nkeys = (u64)total_windows * nbuckets;
+  // one staging block: [ColumnDesc x ncols][u64 x (ncols+1)], copied with a single H2D
+  const size_t desc_bytes = ncols * sizeof(ColumnDesc), start_bytes = (ncols + 1) * sizeof(u64);
+  std::vector<unsigned char> stage(desc_bytes + start_bytes);
+  std::memcpy(stage.data(), cols.data(), desc_bytes);
+  std::memcpy(stage.data() + desc_bytes, col_start.data(), start_bytes);
+  unsigned char* d_stage = (unsigned char*)dev_alloc(stage.size(), s);
+  copy_h2d(d_stage, stage.data(), stage.size(), s);
+#ifndef B200_EMULATE
+  stream_sync(s);  // `stage` is a local; pageable H2D is staged, but be explicit
+#endif
+  const ColumnDesc* d_cols = (const ColumnDesc*)d_stage;
+  const u64* d_col_start = (const u64*)(d_stage + desc_bytes);
+
   u32* d_counts = (u32*)dev_alloc((nkeys + 1) * sizeof(u32), s);
   dev_zero(d_counts, (nkeys + 1) * sizeof(u32), s);
   launch(CountBody{d_cols, d_col_start, ncols, c, nbuckets, d_counts}, total_terms, s);
   exclusive_scan(d_counts, nkeys + 1, s);  // d_counts[nkeys] = number of entries
   u32* d_m = (u32*)dev_alloc(16 * sizeof(u32), s);
   copy_d2d(d_m, d_counts + nkeys, sizeof(u32), s);
-
   u64* d_entries = (u64*)dev_alloc(max_entries * sizeof(u64), s);
   launch(ScatterBody{d_cols, d_col_start, ncols, c, nbuckets, d_counts, d_entries}, total_terms,
          s);
   // d_counts[k] is now the END offset of bucket k
+  launch(WindowUsedBody{d_counts, nbuckets, d_window_used}, plan.total_windows, s);
 
-  Point* d_buckets = (Point*)dev_alloc(nkeys * sizeof(Point), s);
-  launch(FillIdentityBody<C>{d_buckets}, nkeys, s);
-
-  // accumulation cascade
-  {
-    // a chunk of K entries leaves 2 pieces, so K must exceed 2 for the cascade to shrink
-    const u32 chunk1 = opt.chunk1 < 4 ? 4u : opt.chunk1, chunkn = opt.chunkn < 4 ? 4u : opt.chunkn;
-    u64 m_max = max_entries;
-    u32 K = chunk1;
-    const u32* lvl_keys = nullptr;
-    const Point* lvl_pieces = nullptr;
-    u32* m_ptr = d_m;
-    std::vector<void*> to_free;
-    bool first = true;
-    int level = 0;
-    for (;;) {
-      bool final_level = m_max <= K;
-      u64 T = (m_max + K - 1) / K;
-      u32* out_keys = nullptr;
-      Point* out_pieces = nullptr;
-      u32* out_m = d_m + 1 + (level % 8);
-      if (!final_level) {
-        out_keys = (u32*)dev_alloc(2 * T * sizeof(u32), s);
-        out_pieces = (Point*)dev_alloc(2 * T * sizeof(Point), s);
-        to_free.push_back(out_keys);
-        to_free.push_back(out_pieces);
-      }
-      if (first) {
-        KernelTimer::get().begin(s);
-        launch(AccumulateBody<C, true>{nullptr, d_entries, gens, nullptr, m_ptr, K,
-                                       final_level ? 1u : 0u, d_buckets, out_keys, out_pieces,
-                                       out_m},
-               T, s);
-        KernelTimer::get().end(s);
-      } else if (T <= opt.quad_threshold) {
-        launch(AccumulateBody<C, false, QuadExec>{lvl_keys, nullptr, nullptr, lvl_pieces, m_ptr, K,
-                                                  final_level ? 1u : 0u, d_buckets, out_keys,
-                                                  out_pieces, out_m},
-               T * QuadExec::kLanes, s);
-      } else {
-        launch(AccumulateBody<C, false>{lvl_keys, nullptr, nullptr, lvl_pieces, m_ptr, K,
-                                        final_level ? 1u : 0u, d_buckets, out_keys, out_pieces,
-                                        out_m},
-               T, s);
-      }
-      if (final_level)
-        break;
-      first = false;
-      lvl_keys = out_keys;
-      lvl_pieces = out_pieces;
-      m_ptr = out_m;
-      m_max = 2 * T;
-      K = chunkn;
-      ++level;
+  // a chunk of K entries leaves 2 pieces, so K must exceed 2 for the cascade to shrink
+  const u32 chunk1 = opt.chunk1 < 4 ? 4u : opt.chunk1, chunkn = opt.chunkn < 4 ? 4u : opt.chunkn;
+  const u32 into = add_into ? 1u : 0u;
+  u64 m_max = max_entries;
+  u32 K = chunk1;
+  const u32* lvl_keys = nullptr;
+  const Point* lvl_pieces = nullptr;
+  u32* m_ptr = d_m;
+  std::vector<void*> to_free;
+  bool first = true;
+  int level = 0;
+  for (;;) {
+    bool final_level = m_max <= K;
+    u64 T = (m_max + K - 1) / K;
+    u32* out_keys = nullptr;
+    Point* out_pieces = nullptr;
+    u32* out_m = d_m + 1 + (level % 8);
+    if (!final_level) {
+      out_keys = (u32*)dev_alloc(2 * T * sizeof(u32), s);
+      out_pieces = (Point*)dev_alloc(2 * T * sizeof(Point), s);
+      to_free.push_back(out_keys);
+      to_free.push_back(out_pieces);
     }
-    for (void* p : to_free)
-      dev_free(p, s);
+    const u32 fin = final_level ? 1u : 0u;
+    if (first) {
+      KernelTimer::get().begin(s);
+      launch(AccumulateBody<C, true>{nullptr, d_entries, gens, nullptr, m_ptr, K, fin, into,
+                                     d_buckets, out_keys, out_pieces, out_m},
+             T, s);
+      KernelTimer::get().end(s);
+    } else if (T <= opt.quad_threshold) {
+      launch(AccumulateBody<C, false, QuadExec>{lvl_keys, nullptr, nullptr, lvl_pieces, m_ptr, K,
+                                                fin, into, d_buckets, out_keys, out_pieces, out_m},
+             T * QuadExec::kLanes, s);
+    } else {
+      launch(AccumulateBody<C, false>{lvl_keys, nullptr, nullptr, lvl_pieces, m_ptr, K, fin, into,
+                                      d_buckets, out_keys, out_pieces, out_m},
+             T, s);
+    }
+    if (final_level)
+      break;
+    first = false;
+    lvl_keys = out_keys;
+    lvl_pieces = out_pieces;
+    m_ptr = out_m;
+    m_max = 2 * T;
+    K = chunkn;
+    ++level;
   }
+  for (void* ptr : to_free)
+    dev_free(ptr, s);
   dev_free(d_entries, s);
+  dev_free(d_m, s);
+  dev_free(d_counts, s);
+  dev_free(d_stage, s);
+}
 
-  // bucket reduction: nbuckets -> 1 per window
+// Bucket reduction + window combination: out[j] for every column of the plan.
+template <class C>
+void msm_finish(stream_t s, const MsmPlan& plan, const typename C::Point* d_buckets,
+                const u32* d_window_used, typename C::Point* out, const MsmOptions& opt) {
+  typedef typename C::Point Point;
+  const u32 total_windows = plan.total_windows, nbuckets = plan.nbuckets, ncols = plan.ncols;
+  ColumnDesc* d_cols = (ColumnDesc*)dev_alloc(ncols * sizeof(ColumnDesc), s);
+  copy_h2d(d_cols, plan.cols.data(), ncols * sizeof(ColumnDesc), s);
   Point* d_S = nullptr;
-  {
-    u32 m = nbuckets;
-    const Point* X = d_buckets;
-    const Point* Cin = nullptr;
-    std::vector<void*> to_free;
-    if (m == 1) {
-      // c == 1 is never chosen, but keep the degenerate case well-defined
-      d_S = (Point*)dev_alloc(total_windows * sizeof(Point), s);
-      copy_d2d(d_S, d_buckets, total_windows * sizeof(Point), s);
-    }
-    bool first = true;
-    while (m > 1) {
-      u32 g = first ? std::min<u32>(opt.reduce_g1, m) : std::min<u32>(opt.reduce_gn, m);
-      u32 log2g = 0;
-      while ((1u << log2g) < g)
-        ++log2g;
-      u32 m_out = m / g;
-      Point* Xout = (Point*)dev_alloc((u64)total_windows * m_out * sizeof(Point), s);
-      Point* Cout = (Point*)dev_alloc((u64)total_windows * m_out * sizeof(Point), s);
-      if ((u64)total_windows * m_out <= opt.quad_threshold)  // uniform control flow: full-warp shuffles
-        launch(ReduceBody<C, QuadExecConv>{X, Cin, m, g, log2g, Xout, Cout, d_counts, nbuckets},
-               (u64)total_windows * m_out * QuadExec::kLanes, s);
-      else
-        launch(ReduceBody<C>{X, Cin, m, g, log2g, Xout, Cout, d_counts, nbuckets},
-               (u64)total_windows * m_out, s);
-      to_free.push_back(Xout);
-      if (m_out > 1)
-        to_free.push_back(Cout);
-      X = Xout;
-      Cin = Cout;
-      m = m_out;
-      first = false;
-      if (m == 1)
-        d_S = Cout;
-    }
-    for (void* p : to_free)
-      dev_free(p, s);
+  u32 m = nbuckets;
+  const Point* X = d_buckets;
+  const Point* Cin = nullptr;
+  std::vector<void*> to_free;
+  if (m == 1) {  // c == 1 is never chosen, but keep the degenerate case well-defined
+    d_S = (Point*)dev_alloc(total_windows * sizeof(Point), s);
+    copy_d2d(d_S, d_buckets, total_windows * sizeof(Point), s);
   }
+  bool first = true;
+  while (m > 1) {
+    u32 g = first ? std::min<u32>(opt.reduce_g1, m) : std::min<u32>(opt.reduce_gn, m);
+    u32 log2g = 0;
+    while ((1u << log2g) < g)
+      ++log2g;
+    u32 m_out = m / g;
+    Point* Xout = (Point*)dev_alloc((u64)total_windows * m_out * sizeof(Point), s);
+    Point* Cout = (Point*)dev_alloc((u64)total_windows * m_out * sizeof(Point), s);
+    if ((u64)total_windows * m_out <= opt.quad_threshold)  // uniform control flow: full-warp shuffles
+      launch(ReduceBody<C, QuadExecConv>{X, Cin, m, g, log2g, Xout, Cout, d_window_used, nbuckets},
+             (u64)total_windows * m_out * QuadExec::kLanes, s);
+    else
+      launch(ReduceBody<C>{X, Cin, m, g, log2g, Xout, Cout, d_window_used, nbuckets},
+             (u64)total_windows * m_out, s);
+    to_free.push_back(Xout);
+    if (m_out > 1)
+      to_free.push_back(Cout);
+    X = Xout;
+    Cin = Cout;
+    m = m_out;
+    first = false;
+    if (m == 1)
+      d_S = Cout;
+  }
+  for (void* ptr : to_free)
+    dev_free(ptr, s);
   bool uniform_windows = true;  // same Horner trip count in every quad of a warp
   for (u32 j = 1; j < ncols; ++j)
-    uniform_windows = uniform_windows && cols[j].num_windows == cols[0].num_windows;
+    uniform_windows = uniform_windows && plan.cols[j].num_windows == plan.cols[0].num_windows;
   if (ncols <= opt.quad_threshold && uniform_windows)
-    launch(CombineBody<C, QuadExecConv>{d_S, d_cols, c, out}, (u64)ncols * QuadExec::kLanes, s);
+    launch(CombineBody<C, QuadExecConv>{d_S, d_cols, plan.c, out}, (u64)ncols * QuadExec::kLanes,
+           s);
   else if (ncols <= opt.quad_threshold)
-    launch(CombineBody<C, QuadExec>{d_S, d_cols, c, out}, (u64)ncols * QuadExec::kLanes, s);
+    launch(CombineBody<C, QuadExec>{d_S, d_cols, plan.c, out}, (u64)ncols * QuadExec::kLanes, s);
   else
-    launch(CombineBody<C>{d_S, d_cols, c, out}, ncols, s);
+    launch(CombineBody<C>{d_S, d_cols, plan.c, out}, ncols, s);
   dev_free(d_S, s);
-  dev_free(d_buckets, s);
-  dev_free(d_counts, s);
-  dev_free(d_m, s);
-  dev_free(d_col_start, s);
   dev_free(d_cols, s);
+}
+
+// Optional per-range hook: called before the terms [begin, end) are touched (the C-ABI layer uses
+// it to wait for that range's host-to-device copies and to ingest its generators).
+struct RangeHook {
+  virtual void before_range(u64 begin, u64 end) = 0;
+  virtual ~RangeHook() {}
+};
+
+// Computes out[j] = sum_i scalar(j,i) * G_i for every column j. `cols` are host descriptors whose
+// `base` pointers are DEVICE pointers; gens and out are device arrays. The generator range is
+// processed in `num_ranges` contiguous pieces that share one bucket array, so that the sort and
+// accumulation of one piece overlap the arrival of the next. Everything is enqueued on `s`.
+template <class C>
+void msm_run(stream_t s, const typename C::Gen* gens, std::vector<ColumnDesc> cols,
+             typename C::Point* out, const MsmOptions& opt = MsmOptions(), u32 num_ranges = 1,
+             RangeHook* hook = nullptr) {
+  typedef typename C::Point Point;
+  if (cols.empty())
+    return;
+  MsmPlan plan = msm_make_plan(std::move(cols), opt);
+  if (plan.total_terms == 0 || plan.total_windows == 0) {
+    if (hook)
+      hook->before_range(0, plan.max_n);
+    launch(FillIdentityBody<C>{out}, plan.ncols, s);
+    return;
+  }
+  Point* d_buckets = (Point*)dev_alloc(plan.nkeys * sizeof(Point), s);
+  launch(FillIdentityBody<C>{d_buckets}, plan.nkeys, s);
+  u32* d_window_used = (u32*)dev_alloc(plan.total_windows * sizeof(u32), s);
+  dev_zero(d_window_used, plan.total_windows * sizeof(u32), s);
+  if (num_ranges < 1)
+    num_ranges = 1;
+  for (u32 r = 0; r < num_ranges; ++r) {
+    u64 begin = range_begin(plan.max_n, r, num_ranges), end = range_begin(plan.max_n, r + 1, num_ranges);
+    if (hook)
+      hook->before_range(begin, end);
+    msm_accumulate_range<C>(s, plan, gens, begin, end, r > 0, d_buckets, d_window_used, opt);
+  }
+  msm_finish<C>(s, plan, d_buckets, d_window_used, out, opt);
+  dev_free(d_window_used, s);
+  dev_free(d_buckets, s);
 }
 
 }  // namespace b200

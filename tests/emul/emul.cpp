@@ -25,8 +25,10 @@ template <class F> static auto dispatch(unsigned curve_id, F f) {
 }
 
 static MsmOptions g_opt;
+static unsigned g_ranges = 1;
 
 extern "C" {
+void emul_set_ranges(unsigned num_ranges) { g_ranges = num_ranges ? num_ranges : 1; }
 void emul_set_tuning(unsigned window_bits, unsigned chunk1, unsigned chunkn) {
   g_opt.window_bits = window_bits;
   g_opt.chunk1 = chunk1 ? chunk1 : 32;
@@ -38,7 +40,8 @@ void emul_commit(unsigned curve_id, void* out_commitments, uint32_t num,
   if (num == 0) return;
   EngineCtx ctx{0, g_opt, nullptr, 0};
   dispatch(curve_id, [&](auto c) {
-    CurveOps<decltype(c)>::commit_device(ctx, out_commitments, nullptr, num, d, generators, offset);
+    CurveOps<decltype(c)>::commit_device(ctx, out_commitments, nullptr, num, d, generators, offset,
+                                         g_ranges, nullptr, nullptr);
     return 0;
   });
 }
@@ -133,7 +136,8 @@ extern "C" void emul_commit_partial(unsigned curve_id, void* out_partials, uint3
   if (num == 0) return;
   EngineCtx ctx{0, g_opt, nullptr, 0};
   dispatch(curve_id, [&](auto c) {
-    CurveOps<decltype(c)>::commit_device(ctx, nullptr, out_partials, num, d, generators, offset);
+    CurveOps<decltype(c)>::commit_device(ctx, nullptr, out_partials, num, d, generators, offset,
+                                         g_ranges, nullptr, nullptr);
     return 0;
   });
 }

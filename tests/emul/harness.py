@@ -59,6 +59,10 @@ def set_tuning(window_bits=0, chunk1=0, chunkn=0):
     lib().emul_set_tuning(C.c_uint(window_bits), C.c_uint(chunk1), C.c_uint(chunkn))
 
 
+def set_ranges(num_ranges=1):
+    lib().emul_set_ranges(C.c_uint(num_ranges))
+
+
 def commit(curve_id, columns, generators=None, offset=0):
     desc, keep = _desc(columns)
     out = np.zeros((len(columns), SIZES[curve_id][2]), dtype=np.uint8)

@@ -131,3 +131,23 @@ def test_identity_generators_weierstrass(emul, port):
         cols = common.random_columns(rng, 20, [(0, 32, 0), (0, 2, 0)])
         assert stride in (72, 104)
         assert common.same(curve, emul.commit(curve, cols, gens), port.commit(curve, cols, gens))
+
+
+@pytest.mark.parametrize("curve", [0, 2])
+@pytest.mark.parametrize("num_ranges", [2, 3, 7])
+def test_generator_ranges_share_one_bucket_array(emul, port, curve, num_ranges):
+    """The copy-overlap path: the generator range is processed in pieces that add into one bucket
+    array (ragged columns make some pieces empty for some columns)."""
+    rng = np.random.default_rng(curve * 10 + num_ranges)
+    n = 500
+    gens, _ = common.generators_for(port, curve, n)
+    cols = common.random_columns(rng, n, [(0, 32, 0), (-300, 16, 1), (-499, 4, 0), (0, 1, 0)])
+    try:
+        emul.set_ranges(num_ranges)
+        got = emul.commit(curve, cols, gens)
+        got_builtin = emul.commit(0, cols[:2], None, 5) if curve == 0 else None
+    finally:
+        emul.set_ranges(1)
+    assert common.same(curve, got, port.commit(curve, cols, gens))
+    if got_builtin is not None:
+        assert common.same(0, got_builtin, port.commit(0, cols[:2], None, 5))
