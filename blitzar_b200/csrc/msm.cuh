@@ -597,11 +597,7 @@ void msm_accumulate_range(stream_t s, const MsmPlan& plan, const typename C::Gen
   std::vector<unsigned char> stage(desc_bytes + start_bytes);
   std::memcpy(stage.data(), cols.data(), desc_bytes);
   std::memcpy(stage.data() + desc_bytes, col_start.data(), start_bytes);
-  unsigned char* d_stage = (unsigned char*)dev_alloc(stage.size(), s);
-  copy_h2d(d_stage, stage.data(), stage.size(), s);
-#ifndef B200_EMULATE
-  stream_sync(s);  // `stage` is a local; pageable H2D is staged, but be explicit
-#endif
+  unsigned char* d_stage = (unsigned char*)stage_to_device(s, stage.data(), stage.size());
   const ColumnDesc* d_cols = (const ColumnDesc*)d_stage;
   const u64* d_col_start = (const u64*)(d_stage + desc_bytes);
 
@@ -680,8 +676,8 @@ void msm_finish(stream_t s, const MsmPlan& plan, const typename C::Point* d_buck
                 const u32* d_window_used, typename C::Point* out, const MsmOptions& opt) {
   typedef typename C::Point Point;
   const u32 total_windows = plan.total_windows, nbuckets = plan.nbuckets, ncols = plan.ncols;
-  ColumnDesc* d_cols = (ColumnDesc*)dev_alloc(ncols * sizeof(ColumnDesc), s);
-  copy_h2d(d_cols, plan.cols.data(), ncols * sizeof(ColumnDesc), s);
+  ColumnDesc* d_cols =
+      (ColumnDesc*)stage_to_device(s, plan.cols.data(), ncols * sizeof(ColumnDesc));
   Point* d_S = nullptr;
   u32 m = nbuckets;
   const Point* X = d_buckets;

@@ -89,6 +89,44 @@ inline void copy_d2d(void* d, const void* s_, size_t bytes, stream_t s) {
 }
 inline void stream_sync(stream_t s) { B200_CUDA(cudaStreamSynchronize(s)); }
 
+// Small host->device parameter blocks (column descriptors, prefix tables). A pageable
+// cudaMemcpyAsync synchronises the stream, which would stall the launch queue once per range; the
+// blocks therefore go through a ring of pinned slots and are copied truly asynchronously. A slot is
+// reused only after the copy that last read it has completed (per-slot event).
+struct StagingRing {
+  static constexpr size_t kSlotBytes = 16384, kSlots = 256;
+  unsigned char* base = nullptr;
+  cudaEvent_t done[kSlots];
+  size_t next = 0;
+  static StagingRing& get() {
+    static StagingRing r;
+    return r;
+  }
+  void* stage(stream_t s, const void* host, size_t bytes) {
+    void* d = dev_alloc(bytes, s);
+    if (bytes > kSlotBytes) {  // rare (thousands of columns): fall back to a synchronising copy
+      copy_h2d(d, host, bytes, s);
+      stream_sync(s);
+      return d;
+    }
+    if (!base) {
+      B200_CUDA(cudaHostAlloc((void**)&base, kSlotBytes * kSlots, cudaHostAllocDefault));
+      for (auto& e : done) {
+        B200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      }
+    }
+    size_t slot = next++ % kSlots;
+    B200_CUDA(cudaEventSynchronize(done[slot]));
+    std::memcpy(base + slot * kSlotBytes, host, bytes);
+    B200_CUDA(cudaMemcpyAsync(d, base + slot * kSlotBytes, bytes, cudaMemcpyHostToDevice, s));
+    B200_CUDA(cudaEventRecord(done[slot], s));
+    return d;
+  }
+};
+inline void* stage_to_device(stream_t s, const void* host, size_t bytes) {
+  return StagingRing::get().stage(s, host, bytes);
+}
+
 // Optional per-launch timing of the dominant kernel (bucket accumulation, level 1) with CUDA events
 // on the launching stream — used by bench.py for the roofline line; off by default.
 struct KernelTimer {
@@ -160,6 +198,11 @@ inline void copy_h2d(void* d, const void* h, size_t bytes, stream_t) { std::memc
 inline void copy_d2h(void* h, const void* d, size_t bytes, stream_t) { std::memcpy(h, d, bytes); }
 inline void copy_d2d(void* d, const void* s_, size_t bytes, stream_t) { std::memcpy(d, s_, bytes); }
 inline void stream_sync(stream_t) {}
+inline void* stage_to_device(stream_t s, const void* host, size_t bytes) {
+  void* d = dev_alloc(bytes, s);
+  std::memcpy(d, host, bytes);
+  return d;
+}
 struct KernelTimer {
   static KernelTimer& get() {
     static KernelTimer t;
