@@ -586,7 +586,7 @@ void b200_profile_read(float* total_ms, unsigned* launches) {
 void b200_set_tuning(unsigned window_bits, unsigned chunk1, unsigned chunkn) {
   std::lock_guard<std::mutex> lock(g_mutex);
   g_state.opt.window_bits = window_bits;
-  g_state.opt.chunk1 = chunk1 ? chunk1 : 32;
+  g_state.opt.chunk1 = chunk1;
   g_state.opt.chunkn = chunkn ? chunkn : 8;
 }
 

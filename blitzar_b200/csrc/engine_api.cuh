@@ -10,7 +10,7 @@ namespace b200 {
 
 struct MsmOptions {
   u32 window_bits = 0;  // 0 = choose from n
-  u32 chunk1 = 32;      // chunk length of the first accumulation level
+  u32 chunk1 = 0;       // chunk length of the first accumulation level (0 = 32, or 64 for big passes)
   u32 chunkn = 8;       // chunk length of the cascade levels
   u32 reduce_g1 = 16;   // bucket-reduction group size, first level (power of two)
   u32 reduce_gn = 4;    // bucket-reduction group size, later levels (power of two)

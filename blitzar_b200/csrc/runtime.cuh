@@ -43,7 +43,15 @@ namespace b200 {
 
 typedef cudaStream_t stream_t;
 
-template <class Body> __global__ void __launch_bounds__(Body::kBlock) k_run(Body body, u64 n) {
+// bodies may request a minimum number of resident blocks per SM (register cap) with kMinBlocks
+template <class Body, class = void> struct MinBlocks {
+  static constexpr int value = 1;
+};
+template <class Body> struct MinBlocks<Body, decltype((void)Body::kMinBlocks)> {
+  static constexpr int value = Body::kMinBlocks;
+};
+template <class Body>
+__global__ void __launch_bounds__(Body::kBlock, MinBlocks<Body>::value) k_run(Body body, u64 n) {
   u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid < n)
     body(tid);

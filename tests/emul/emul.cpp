@@ -31,7 +31,7 @@ extern "C" {
 void emul_set_ranges(unsigned num_ranges) { g_ranges = num_ranges ? num_ranges : 1; }
 void emul_set_tuning(unsigned window_bits, unsigned chunk1, unsigned chunkn) {
   g_opt.window_bits = window_bits;
-  g_opt.chunk1 = chunk1 ? chunk1 : 32;
+  g_opt.chunk1 = chunk1;
   g_opt.chunkn = chunkn ? chunkn : 8;
 }
 // same contract as b200_commit_device, with host pointers standing in for device pointers
