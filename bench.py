@@ -207,6 +207,10 @@ def run_cuda(args, rank, local_rank, world):
     d_out = torch.zeros((64,), dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
 
+    # the library's stream as a torch stream: NCCL collectives issued under it are ordered against the
+    # engine's kernels on the device, without host synchronisation
+    lib_stream = torch.cuda.ExternalStream(bb.stream_ptr(), device=torch.device("cuda", local_rank))
+
     def barrier():
         bb.synchronize()
         torch.cuda.synchronize()
@@ -222,9 +226,8 @@ def run_cuda(args, rank, local_rank, world):
         else:
             bb.commit_device(curve, [(n, 32, 0)], [d_scal.data_ptr()], d_gens.data_ptr(), None,
                              d_partial.data_ptr())
-            bb.synchronize()
-            dist.all_gather_into_tensor(d_all.view(-1), d_partial)
-            torch.cuda.synchronize()
+            with torch.cuda.stream(lib_stream):
+                dist.all_gather_into_tensor(d_all.view(-1), d_partial)
             bb.combine_partials_device(curve, d_out.data_ptr(), d_all.data_ptr(), world, 1)
 
     def step_e2e():

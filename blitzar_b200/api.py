@@ -35,7 +35,7 @@ B200_SYMBOLS = [
     "b200_event_record", "b200_event_elapsed_ms", "b200_event_destroy", "b200_commit_device",
     "b200_combine_partials_device", "b200_fixed_msm_device",
     "b200_combine_partials_projective_device", "b200_set_tuning", "b200_profile_accumulate",
-    "b200_profile_read", "b200_set_reduce_groups",
+    "b200_profile_read", "b200_set_reduce_groups", "b200_stream",
 ]
 
 
@@ -68,6 +68,7 @@ def lib():
         L.b200_point_bytes.restype = C.c_uint
         L.b200_malloc.restype = C.c_void_p
         L.b200_event_create.restype = C.c_void_p
+        L.b200_stream.restype = C.c_void_p
         L.b200_event_elapsed_ms.restype = C.c_float
         _lib = L
     return _lib
@@ -291,3 +292,8 @@ def point_bytes(curve_id):
 
 def set_reduce_groups(g1=0, gn=0):
     lib().b200_set_reduce_groups(C.c_uint(g1), C.c_uint(gn))
+
+
+def stream_ptr():
+    """cudaStream_t of the library (int), e.g. for torch.cuda.ExternalStream."""
+    return int(lib().b200_stream())

@@ -490,6 +490,10 @@ void b200_memcpy_d2h(void* h, const void* d, uint64_t bytes) {
   copy_d2h(h, d, bytes, g_state.stream);
   stream_sync(g_state.stream);
 }
+void* b200_stream(void) {
+  require_init("b200_stream");
+  return (void*)g_state.stream;
+}
 void b200_synchronize(void) {
   std::lock_guard<std::mutex> lock(g_mutex);
   require_init("b200_synchronize");

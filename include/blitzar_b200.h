@@ -164,6 +164,9 @@ void b200_free(void* device_ptr);
 void b200_memcpy_h2d(void* device_dst, const void* host_src, uint64_t bytes);
 void b200_memcpy_d2h(void* host_dst, const void* device_src, uint64_t bytes);
 void b200_synchronize(void);
+/* The cudaStream_t every kernel of the engine is launched on (e.g. to wrap it as an external stream
+ * of another runtime so that collectives can be ordered against it without host synchronisation). */
+void* b200_stream(void);
 /* CUDA events on the library's stream (the stream every kernel of the engine is launched on). */
 void* b200_event_create(void);
 void b200_event_record(void* event);
