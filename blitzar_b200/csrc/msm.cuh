@@ -262,6 +262,23 @@ template <class C> struct FillIdentityBody {
   B200_HD void operator()(u64 t) const { p[t] = C::identity(); }
 };
 
+// Accumulator of the gathering level: the curve's Point, or its FP64-pipe form where the curve
+// provides one (ed25519).
+template <class C, class X, bool kFp64> struct GatherAcc {
+  typename C::Point p;
+  B200_HD void start(const typename C::Gen& g, bool negate) { C::gen_to_point(p, g, negate); }
+  B200_HD void add(const typename C::Gen& g, bool negate) {
+    C::template add_gen<X>(p, p, g, negate);
+  }
+  B200_HD void get(typename C::Point& out) const { out = p; }
+};
+template <class C, class X> struct GatherAcc<C, X, true> {
+  typename C::AccD a;
+  B200_HD void start(const typename C::Gen& g, bool negate) { C::accd_from_gen(a, g, negate); }
+  B200_HD void add(const typename C::Gen& g, bool negate) { C::accd_add_gen(a, g, negate); }
+  B200_HD void get(typename C::Point& out) const { C::accd_to_point(out, a); }
+};
+
 // Chunk walk. Thread t sums entries [t*K, (t+1)*K) of the sorted list. Segments (runs of one key)
 // strictly inside the chunk are complete and go straight to buckets[key]; the first and last
 // segment may continue in the neighbouring chunks, so they are emitted as pieces (2 per chunk,
@@ -330,6 +347,7 @@ template <class C, bool kGather, class X = SeqExec> struct AccumulateBody {
       u64 ent = entries[b];
       typename C::Gen g = gens[(u32)ent >> 1];
       cur = (u32)(ent >> 32);
+      GatherAcc<C, X, C::kFp64Accumulate> ga;
       for (u64 i = b; i < e; ++i) {
         u64 ent_n = ent;
         typename C::Gen g_n = g;
@@ -340,10 +358,11 @@ template <class C, bool kGather, class X = SeqExec> struct AccumulateBody {
         const u32 k = (u32)(ent >> 32);
         const bool negate = ((u32)ent & 1u) != 0;
         if (i == b) {
-          C::gen_to_point(acc, g, negate);
+          ga.start(g, negate);
         } else if (k == cur) {
-          C::template add_gen<X>(acc, acc, g, negate);
+          ga.add(g, negate);
         } else {
+          ga.get(acc);
           if (final_level || !first_seg) {
             put_bucket_guarded(cur, acc, writer);
           } else if (writer) {
@@ -352,11 +371,12 @@ template <class C, bool kGather, class X = SeqExec> struct AccumulateBody {
           }
           first_seg = false;
           cur = k;
-          C::gen_to_point(acc, g, negate);
+          ga.start(g, negate);
         }
         ent = ent_n;
         g = g_n;
       }
+      ga.get(acc);
     } else {
       cur = key_at(b);
       fetch(acc, b, true);

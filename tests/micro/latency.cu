@@ -39,6 +39,54 @@ template <int OP> __global__ void k_thr(Fe<8>* io, int iters) {
   }
   if (a.l[0] == 0x12345678u) io[8] = a;
 }
+__global__ void k_thr_fp64(Fe<8>* io, int iters) {
+  Fe<8> a8, b8;
+  F25519::canonical(a8, io[threadIdx.x & 3]);
+  F25519::canonical(b8, io[4 + (threadIdx.x & 3)]);
+  FeD a, b;
+  F25519D::from_fe(a, a8);
+  F25519D::from_fe(b, b8);
+  long long ta[5], tb[5];
+  for (int i = 0; i < 5; ++i) { ta[i] = a.l[i]; tb[i] = b.l[i]; }
+  F25519D::carry(a, ta);
+  F25519D::carry(b, tb);
+  double db[5];
+  for (int i = 0; i < 5; ++i) db[i] = F25519D::to_double(b.l[i]);
+  for (int it = 0; it < iters; ++it) {
+    double da[5];
+    for (int i = 0; i < 5; ++i) da[i] = F25519D::to_double(a.l[i]);
+    F25519D::mul(a, da, db);
+  }
+  if (a.l[0] == 0x12345678) io[8].l[0] = (u32)a.l[1];
+}
+__global__ void k_thr_accd(Fe<8>* io, int iters) {
+  Ed25519::Gen g;
+  F25519::canonical(g.YpX, io[0]); F25519::canonical(g.YmX, io[1]); F25519::canonical(g.Z2, io[2]); F25519::canonical(g.T2d, io[3]);
+  Ed25519::AccD acc;
+  Ed25519::accd_from_gen(acc, g, false);
+  for (int it = 0; it < iters; ++it) Ed25519::accd_add_gen(acc, g, (it & 1) != 0);
+  if (acc.X.l[0] == 0x12345678) io[8].l[0] = (u32)acc.Y.l[1];
+}
+__global__ void k_thr_addgen(Fe<8>* io, int iters) {
+  Ed25519::Gen g;
+  g.YpX = io[0]; g.YmX = io[1]; g.Z2 = io[2]; g.T2d = io[3];
+  Ed25519::Point acc;
+  Ed25519::gen_to_point(acc, g, false);
+  for (int it = 0; it < iters; ++it) Ed25519::add_gen<SeqExec>(acc, acc, g, (it & 1) != 0);
+  if (acc.X.l[0] == 0x12345678) io[8] = acc.Y;
+}
+template <class K> void thr_k(const char* name, K kern, Fe<8>* d, int threads, int blocks_per_sm) {
+  const int iters = 1000, blocks = 148 * blocks_per_sm;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  kern<<<blocks, threads>>>(d, iters);
+  cudaEventRecord(e0);
+  kern<<<blocks, threads>>>(d, iters);
+  cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  double ops = (double)blocks * threads * iters;
+  printf("throughput %-30s %d thr x %d blk/SM: %.2f G op/s (%.1f SM-cycles per warp-op)\n", name, threads, blocks_per_sm,
+         ops / ms * 1e-6, 1.965e9 * 148 / (ops / 32 / (ms * 1e-3)));
+}
 template <int OP> void lat(const char* name, Fe<8>* d, long long* dc, int threads) {
   const int iters = 200;
   k_lat<OP><<<1, threads>>>(d, dc, iters);
@@ -78,6 +126,12 @@ int main() {
   thr<0>("F25519::mul (chains)", d);
   thr<1>("F25519::mul_lat (columns)", d);
   thr<2>("F25519::mul_ref (plain C)", d);
+  thr_k("F25519D::mul (fp64 pipe)", k_thr_fp64, d, 256, 8);
+  thr_k("F25519D::mul (fp64 pipe)", k_thr_fp64, d, 128, 3);
+  thr_k("accd_add_gen (fp64 point add)", k_thr_accd, d, 128, 3);
+  thr_k("accd_add_gen (fp64 point add)", k_thr_accd, d, 128, 6);
+  thr_k("add_gen (integer point add)", k_thr_addgen, d, 128, 3);
+  thr_k("add_gen (integer point add)", k_thr_addgen, d, 128, 6);
   printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
   return 0;
 }
