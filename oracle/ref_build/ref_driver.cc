@@ -53,7 +53,13 @@
 #include "sxt/multiexp/pippenger2/in_memory_partition_table_accessor_utility.h"
 #include "sxt/multiexp/pippenger2/multiexponentiation.h"
 #include "sxt/multiexp/pippenger2/variable_length_multiexponentiation.h"
+#include "sxt/base/num/ceil_log2.h"
+#include "sxt/proof/inner_product/cpu_driver.h"
+#include "sxt/proof/inner_product/proof_computation.h"
+#include "sxt/proof/inner_product/proof_descriptor.h"
+#include "sxt/proof/transcript/transcript.h"
 #include "sxt/ristretto/base/byte_conversion.h"
+#include "sxt/scalar25/type/element.h"
 #include "sxt/ristretto/operation/compression.h"
 #include "sxt/ristretto/type/compressed_element.h"
 #include "sxt/seqcommit/generator/base_element.h"
@@ -309,6 +315,65 @@ void ref_fixed_msm(unsigned curve_id, void* res, const void* generators, unsigne
                                                         num_outputs, n, scalars);
     break;
   }
+}
+
+// A fresh Merlin transcript with the given label, as a caller of the proof API creates it
+// (sxt/proof/transcript/transcript.cc:41-53); 203 bytes.
+void ref_transcript_new(uint8_t* transcript203, const char* label) {
+  prft::transcript t{label};
+  static_assert(sizeof(prft::transcript) == 203);
+  std::memcpy(transcript203, &t, 203);
+}
+// Draw a 32-byte challenge (used by tests to check that two transcripts are in the same state)
+void ref_transcript_challenge(uint8_t* out32, uint8_t* transcript203, const char* label) {
+  auto& t = *reinterpret_cast<prft::transcript*>(transcript203);
+  t.challenge_bytes({out32, 32}, label);
+}
+
+// cbindings/inner_product_proof.cc:101-130 with the cpu backend (cpu_backend.cc:171-181)
+void ref_prove_inner_product(uint8_t* l_vector, uint8_t* r_vector, uint8_t* ap_value,
+                             uint8_t* transcript203, uint64_t n, uint64_t generators_offset,
+                             const uint8_t* a_vector, const uint8_t* b_vector) {
+  auto n_lg2 = static_cast<size_t>(basn::ceil_log2(n));
+  auto np = 1ull << n_lg2;
+  std::vector<c21t::element_p3> gens(np + 1);
+  sqcgn::cpu_get_generators(gens, generators_offset);
+  prfip::proof_descriptor descriptor{
+      .b_vector = {reinterpret_cast<const s25t::element*>(b_vector), n},
+      .g_vector = {gens.data(), np},
+      .q_value = gens.data() + np};
+  prfip::cpu_driver drv;
+  auto fut = prfip::prove_inner_product(
+      {reinterpret_cast<rstt::compressed_element*>(l_vector), n_lg2},
+      {reinterpret_cast<rstt::compressed_element*>(r_vector), n_lg2},
+      *reinterpret_cast<s25t::element*>(ap_value),
+      *reinterpret_cast<prft::transcript*>(transcript203), drv, descriptor,
+      {reinterpret_cast<const s25t::element*>(a_vector), n});
+  (void)fut;
+}
+
+// cbindings/inner_product_proof.cc:135-167 with the cpu backend (cpu_backend.cc:186-198)
+int ref_verify_inner_product(uint8_t* transcript203, uint64_t n, uint64_t generators_offset,
+                             const uint8_t* b_vector, const uint8_t* product,
+                             const uint8_t* a_commit160, const uint8_t* l_vector,
+                             const uint8_t* r_vector, const uint8_t* ap_value) {
+  auto n_lg2 = static_cast<size_t>(basn::ceil_log2(n));
+  auto np = 1ull << n_lg2;
+  std::vector<c21t::element_p3> gens(np + 1);
+  sqcgn::cpu_get_generators(gens, generators_offset);
+  prfip::proof_descriptor descriptor{
+      .b_vector = {reinterpret_cast<const s25t::element*>(b_vector), n},
+      .g_vector = {gens.data(), np},
+      .q_value = gens.data() + np};
+  prfip::cpu_driver drv;
+  return prfip::verify_inner_product(
+             *reinterpret_cast<prft::transcript*>(transcript203), drv, descriptor,
+             *reinterpret_cast<const s25t::element*>(product),
+             *reinterpret_cast<const c21t::element_p3*>(a_commit160),
+             {reinterpret_cast<const rstt::compressed_element*>(l_vector), n_lg2},
+             {reinterpret_cast<const rstt::compressed_element*>(r_vector), n_lg2},
+             *reinterpret_cast<const s25t::element*>(ap_value))
+      .value();
 }
 
 // sizes the tests rely on (sizeof of the reference types)
