@@ -297,3 +297,33 @@ def set_reduce_groups(g1=0, gn=0):
 def stream_ptr():
     """cudaStream_t of the library (int), e.g. for torch.cuda.ExternalStream."""
     return int(lib().b200_stream())
+
+
+def prove_inner_product(transcript, a, b, generators_offset=0):
+    """sxt_curve25519_prove_inner_product. transcript: uint8[203] (advanced in place); a, b:
+    uint8 [n, 32] scalars. Returns (l_vector [rounds, 32], r_vector, ap_value [32])."""
+    n = a.shape[0]
+    rounds = max(0, (n - 1).bit_length())
+    lv = np.zeros((max(rounds, 1), 32), dtype=np.uint8)
+    rv = np.zeros((max(rounds, 1), 32), dtype=np.uint8)
+    ap = np.zeros(32, dtype=np.uint8)
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    b = np.ascontiguousarray(b, dtype=np.uint8)
+    lib().sxt_curve25519_prove_inner_product(_ptr(lv), _ptr(rv), _ptr(ap), _ptr(transcript),
+                                             C.c_uint64(n), C.c_uint64(generators_offset),
+                                             _ptr(a), _ptr(b))
+    return lv[:rounds], rv[:rounds], ap
+
+
+def verify_inner_product(transcript, b, product, a_commit, l_vector, r_vector, ap_value,
+                         generators_offset=0):
+    """sxt_curve25519_verify_inner_product -> 1 / 0."""
+    n = b.shape[0]
+    b = np.ascontiguousarray(b, dtype=np.uint8)
+    lv = np.ascontiguousarray(l_vector if len(l_vector) else np.zeros((1, 32), np.uint8))
+    rv = np.ascontiguousarray(r_vector if len(r_vector) else np.zeros((1, 32), np.uint8))
+    lib().sxt_curve25519_verify_inner_product.restype = C.c_int
+    return int(lib().sxt_curve25519_verify_inner_product(
+        _ptr(transcript), C.c_uint64(n), C.c_uint64(generators_offset), _ptr(b),
+        _ptr(np.ascontiguousarray(product)), _ptr(np.ascontiguousarray(a_commit)), _ptr(lv),
+        _ptr(rv), _ptr(np.ascontiguousarray(ap_value))))

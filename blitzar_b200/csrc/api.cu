@@ -340,23 +340,51 @@ int sxt_curve25519_get_one_commit(struct sxt_ristretto255* one_commit, uint64_t 
   return 0;
 }
 
-void sxt_curve25519_prove_inner_product(struct sxt_ristretto255_compressed*,
-                                        struct sxt_ristretto255_compressed*,
-                                        struct sxt_curve25519_scalar*, struct sxt_transcript*,
-                                        uint64_t, uint64_t, const struct sxt_curve25519_scalar*,
-                                        const struct sxt_curve25519_scalar*) {
-  die("sxt_curve25519_prove_inner_product is not provided by blitzar_b200 (MSM hot path only)",
-      __FILE__, __LINE__);
+// blitzar_api.h:566 — checks as cbindings/inner_product_proof.cc:34-58
+void sxt_curve25519_prove_inner_product(struct sxt_ristretto255_compressed* l_vector,
+                                        struct sxt_ristretto255_compressed* r_vector,
+                                        struct sxt_curve25519_scalar* ap_value,
+                                        struct sxt_transcript* transcript, uint64_t n,
+                                        uint64_t generators_offset,
+                                        const struct sxt_curve25519_scalar* a_vector,
+                                        const struct sxt_curve25519_scalar* b_vector) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  require_init("sxt_curve25519_prove_inner_product");
+  B200_REQUIRE(transcript != nullptr, "transcript must not be null");
+  B200_REQUIRE(ap_value != nullptr, "ap_value must not be null");
+  B200_REQUIRE(b_vector != nullptr && a_vector != nullptr, "a_vector / b_vector must not be null");
+  B200_REQUIRE(n > 0, "a_vector and b_vector lengths must be greater than zero");
+  B200_REQUIRE(n == 1 || (l_vector != nullptr && r_vector != nullptr),
+               "l_vector and r_vector must not be null when n > 1");
+  B200_REQUIRE(n < (1ull << 30), "n too large");
+  ipa_prove(ctx(), reinterpret_cast<uint8_t*>(l_vector), reinterpret_cast<uint8_t*>(r_vector),
+            ap_value->bytes, transcript->bytes, n, generators_offset,
+            reinterpret_cast<const uint8_t*>(a_vector), reinterpret_cast<const uint8_t*>(b_vector));
 }
-int sxt_curve25519_verify_inner_product(struct sxt_transcript*, uint64_t, uint64_t,
-                                        const struct sxt_curve25519_scalar*,
-                                        const struct sxt_curve25519_scalar*,
-                                        const struct sxt_ristretto255*,
-                                        const struct sxt_ristretto255_compressed*,
-                                        const struct sxt_ristretto255_compressed*,
-                                        const struct sxt_curve25519_scalar*) {
-  die("sxt_curve25519_verify_inner_product is not provided by blitzar_b200 (MSM hot path only)",
-      __FILE__, __LINE__);
+// blitzar_api.h:611 — 1 if the proof verifies, 0 otherwise
+int sxt_curve25519_verify_inner_product(struct sxt_transcript* transcript, uint64_t n,
+                                        uint64_t generators_offset,
+                                        const struct sxt_curve25519_scalar* b_vector,
+                                        const struct sxt_curve25519_scalar* product,
+                                        const struct sxt_ristretto255* a_commit,
+                                        const struct sxt_ristretto255_compressed* l_vector,
+                                        const struct sxt_ristretto255_compressed* r_vector,
+                                        const struct sxt_curve25519_scalar* ap_value) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  require_init("sxt_curve25519_verify_inner_product");
+  B200_REQUIRE(transcript != nullptr, "transcript must not be null");
+  B200_REQUIRE(ap_value != nullptr && product != nullptr && a_commit != nullptr &&
+                   b_vector != nullptr,
+               "ap_value / product / a_commit / b_vector must not be null");
+  B200_REQUIRE(n > 0, "b_vector length must be greater than zero");
+  B200_REQUIRE(n == 1 || (l_vector != nullptr && r_vector != nullptr),
+               "l_vector and r_vector must not be null when n > 1");
+  B200_REQUIRE(n < (1ull << 30), "n too large");
+  return ipa_verify(ctx(), transcript->bytes, n, generators_offset,
+                    reinterpret_cast<const uint8_t*>(b_vector), product->bytes,
+                    reinterpret_cast<const uint8_t*>(a_commit),
+                    reinterpret_cast<const uint8_t*>(l_vector),
+                    reinterpret_cast<const uint8_t*>(r_vector), ap_value->bytes);
 }
 void sxt_prove_sumcheck(void*, void*, unsigned, const struct sumcheck_descriptor*, void*, void*) {
   die("sxt_prove_sumcheck is not provided by blitzar_b200 (MSM hot path only)", __FILE__,

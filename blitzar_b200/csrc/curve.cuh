@@ -399,6 +399,44 @@ struct Ed25519 {
     F::to_bytes((unsigned char*)dst, s_);
   }
 
+  // ristretto255 decoding (RFC 9496 §4.3.1); same contract as rstb::from_bytes
+  // (sxt/ristretto/base/byte_conversion.cc:135-). Returns false for a non-canonical / invalid
+  // encoding (p is then unspecified).
+  static B200_HD bool decode(Point& p, const unsigned char* bytes) {
+    fe s, ss, u1, u2, u2sq, v, t, inv_sqrt, den_x, den_y, chk;
+    const fe one = F::one();
+    F::from_bytes(s, bytes);
+    // canonical (re-encoding reproduces the bytes, top bit clear) and non-negative
+    unsigned char back[32];
+    F::to_bytes(back, s);
+    bool canonical = true;
+    for (int i = 0; i < 32; ++i)
+      canonical = canonical && (back[i] == bytes[i]);
+    if (!canonical || (bytes[0] & 1))
+      return false;
+    F::sqr(ss, s);
+    F::sub(u1, one, ss);
+    F::add(u2, one, ss);
+    F::sqr(u2sq, u2);
+    F::sqr(t, u1);
+    F::mul(t, t, F::constant([](int i) { return F25_D(i); }));
+    F::neg(v, t);
+    F::sub(v, v, u2sq);
+    F::mul(t, v, u2sq);
+    int was_square = sqrt_ratio_m1(inv_sqrt, one, t);
+    F::mul(den_x, inv_sqrt, u2);
+    F::mul(den_y, inv_sqrt, den_x);
+    F::mul(den_y, den_y, v);
+    F::mul(p.X, s, den_x);
+    F::dbl(p.X, p.X);
+    F::abs(p.X, p.X);
+    F::mul(p.Y, u1, den_y);
+    p.Z = one;
+    F::mul(p.T, p.X, p.Y);
+    chk = p.Y;
+    return was_square && !F::is_negative(p.T) && !F::is_zero(chk);
+  }
+
   // ristretto255 one-way map half (RFC 9496 §4.3.4 MAP); same as rstb::apply_elligator
   // (sxt/ristretto/base/elligator.cc:47-93).
   static B200_HD void elligator(Point& p, const fe& t) {

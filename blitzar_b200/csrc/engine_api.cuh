@@ -66,6 +66,15 @@ struct CurveVTable {
 };
 extern const CurveVTable kVTableEd25519, kVTableBls12381, kVTableBn254, kVTableGrumpkin;
 
+// inner-product argument over ristretto255 (ipa.cuh); same contracts as the two sxt_* entry points
+void ipa_prove(const EngineCtx& ctx, uint8_t* l_vector, uint8_t* r_vector, uint8_t* ap_value,
+               uint8_t* transcript203, uint64_t n, uint64_t generators_offset,
+               const uint8_t* a_vector, const uint8_t* b_vector);
+int ipa_verify(const EngineCtx& ctx, uint8_t* transcript203, uint64_t n,
+               uint64_t generators_offset, const uint8_t* b_vector, const uint8_t* product,
+               const uint8_t* a_commit160, const uint8_t* l_vector, const uint8_t* r_vector,
+               const uint8_t* ap_value);
+
 // built-in ristretto generators g(first .. first+n) into the device generator layout
 void launch_builtin_generators(const EngineCtx& ctx, void* gens, uint64_t first, uint64_t n);
 

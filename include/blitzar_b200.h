@@ -104,8 +104,9 @@ int sxt_ristretto255_get_generators(struct sxt_ristretto255* generators, uint64_
 /* blitzar_api.h:477. one_commit = g(0) + ... + g(n-1) (identity for n = 0) */
 int sxt_curve25519_get_one_commit(struct sxt_ristretto255* one_commit, uint64_t n);
 
-/* blitzar_api.h:566 / :611. Inner-product argument: declared for ABI completeness; not part of the
- * round-1 hot path — calling them aborts with a message. */
+/* blitzar_api.h:566 / :611. Inner-product argument over g(generators_offset ..) with Q = g[np],
+ * np = 2^ceil(log2 n); `transcript` is the caller's Merlin transcript (203 bytes), advanced in
+ * place exactly as the reference advances it. verify returns 1 / 0. */
 void sxt_curve25519_prove_inner_product(struct sxt_ristretto255_compressed* l_vector,
                                         struct sxt_ristretto255_compressed* r_vector,
                                         struct sxt_curve25519_scalar* ap_value,

@@ -12,6 +12,7 @@
 #include <cstdint>
 struct uint4 { uint32_t x, y, z, w; };
 #include "../../blitzar_b200/csrc/engine.cuh"
+#include "../../blitzar_b200/csrc/ipa.cuh"
 
 using namespace b200;
 
@@ -194,4 +195,20 @@ extern "C" int emul_check_fp64(unsigned iters, unsigned seed) {
     for (int i = 0; i < 5; ++i) if (r.l[i] > (1LL << 50) + (1LL << 14) || r.l[i] < -(1LL << 50) - (1LL << 14)) { ++bad; break; }
   }
   return bad;
+}
+
+// inner-product argument through the emulated kernels (same contracts as the sxt_* entry points)
+extern "C" void emul_prove_inner_product(uint8_t* l_vector, uint8_t* r_vector, uint8_t* ap_value,
+                                         uint8_t* transcript203, uint64_t n, uint64_t offset,
+                                         const uint8_t* a_vector, const uint8_t* b_vector) {
+  EngineCtx ctx{0, g_opt, nullptr, 0};
+  Ipa::prove(ctx, l_vector, r_vector, ap_value, transcript203, n, offset, a_vector, b_vector);
+}
+extern "C" int emul_verify_inner_product(uint8_t* transcript203, uint64_t n, uint64_t offset,
+                                         const uint8_t* b_vector, const uint8_t* product,
+                                         const uint8_t* a_commit160, const uint8_t* l_vector,
+                                         const uint8_t* r_vector, const uint8_t* ap_value) {
+  EngineCtx ctx{0, g_opt, nullptr, 0};
+  return Ipa::verify(ctx, transcript203, n, offset, b_vector, product, a_commit160, l_vector,
+                     r_vector, ap_value);
 }

@@ -119,3 +119,33 @@ def fixed_msm(curve_id, generators_p, num_outputs, n, scalars, element_num_bytes
 
 def check_mul(field_id, iters=2000, seed=1):
     return int(lib().emul_check_mul(C.c_uint(field_id), C.c_uint(iters), C.c_uint(seed)))
+
+
+def prove_inner_product(transcript, a, b, generators_offset=0):
+    """Emulated sxt_curve25519_prove_inner_product; returns (l_vector, r_vector, ap_value)."""
+    n = a.shape[0]
+    rounds = max(0, (n - 1).bit_length())
+    lv = np.zeros((max(rounds, 1), 32), dtype=np.uint8)
+    rv = np.zeros((max(rounds, 1), 32), dtype=np.uint8)
+    ap = np.zeros(32, dtype=np.uint8)
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    b = np.ascontiguousarray(b, dtype=np.uint8)
+    lib().emul_prove_inner_product(C.c_void_p(lv.ctypes.data), C.c_void_p(rv.ctypes.data),
+                                   C.c_void_p(ap.ctypes.data), C.c_void_p(transcript.ctypes.data),
+                                   C.c_uint64(n), C.c_uint64(generators_offset),
+                                   C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data))
+    return lv[:rounds], rv[:rounds], ap
+
+
+def verify_inner_product(transcript, b, product, a_commit, l_vector, r_vector, ap_value,
+                         generators_offset=0):
+    n = b.shape[0]
+    b = np.ascontiguousarray(b, dtype=np.uint8)
+    lv = np.ascontiguousarray(l_vector if len(l_vector) else np.zeros((1, 32), np.uint8))
+    rv = np.ascontiguousarray(r_vector if len(r_vector) else np.zeros((1, 32), np.uint8))
+    lib().emul_verify_inner_product.restype = C.c_int
+    return int(lib().emul_verify_inner_product(
+        C.c_void_p(transcript.ctypes.data), C.c_uint64(n), C.c_uint64(generators_offset),
+        C.c_void_p(b.ctypes.data), C.c_void_p(np.ascontiguousarray(product).ctypes.data),
+        C.c_void_p(np.ascontiguousarray(a_commit).ctypes.data), C.c_void_p(lv.ctypes.data),
+        C.c_void_p(rv.ctypes.data), C.c_void_p(np.ascontiguousarray(ap_value).ctypes.data)))

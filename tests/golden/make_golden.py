@@ -54,3 +54,33 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def make_inner_product_fixture():
+    """tests/golden/inner_product.npz: proofs produced by the reference's cpu backend
+    (sxt_curve25519_prove_inner_product semantics) for n = 1, 2, 5, 16, 37 with a transcript
+    labelled b"golden-ipa" and generators_offset = 11: inputs, the transcript before / after, the
+    proof, <a,b> and the commitment <a, G> that the verifier takes."""
+    L = 2**252 + 27742317777372353535851937790883648493
+    rng = np.random.default_rng(777)
+    out = {}
+    cases = [1, 2, 5, 16, 37]
+    for ci, n in enumerate(cases):
+        av = [int.from_bytes(rng.bytes(32), "little") % L for _ in range(n)]
+        bv = [int.from_bytes(rng.bytes(32), "little") % L for _ in range(n)]
+        a = np.array([list(v.to_bytes(32, "little")) for v in av], dtype=np.uint8)
+        b = np.array([list(v.to_bytes(32, "little")) for v in bv], dtype=np.uint8)
+        t0 = refcpu.transcript_new(b"golden-ipa")
+        t = t0.copy()
+        lv, rv, ap = refcpu.prove_inner_product(t, a, b, generators_offset=11)
+        prod = sum(x * y for x, y in zip(av, bv)) % L
+        np_ = 1 << max(0, (n - 1).bit_length())
+        g = refcpu.ristretto_generators(np_, 11)
+        acommit = refcpu.fixed_msm(0, g[:n], 1, n, a, element_num_bytes=32)[0]
+        out.update({f"n{ci}": n, f"a{ci}": a, f"b{ci}": b, f"t0_{ci}": t0, f"t1_{ci}": t,
+                    f"l{ci}": lv, f"r{ci}": rv, f"ap{ci}": ap,
+                    f"product{ci}": np.array(list(prod.to_bytes(32, "little")), dtype=np.uint8),
+                    f"acommit{ci}": acommit})
+    out["num_cases"] = len(cases)
+    out["generators_offset"] = 11
+    np.savez_compressed(os.path.join(HERE, "inner_product.npz"), **out)
