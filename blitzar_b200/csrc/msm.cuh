@@ -574,11 +574,17 @@ template <class C> struct SumPartsBody {
 };
 
 // ---- host orchestration --------------------------------------------------------------------------
-inline u32 choose_window_bits(u64 max_n, u32 max_width) {
+// c minimising (windows) x (terms + bucket-reduction work), with the bucket arrays of all columns
+// capped at kMaxBucketBytes of HBM. Large single-column calls get c up to 20 (2^19 buckets per
+// window: fewer additions per term; the reduction is amortised over 2^23+ terms).
+inline u32 choose_window_bits(u64 max_n, u32 max_width, u32 ncols, size_t point_bytes) {
+  const double kMaxBucketBytes = 3.0e9;
   u32 best = 2;
   double best_cost = 1e300;
-  for (u32 c = 2; c <= 16; ++c) {
+  for (u32 c = 2; c <= 20; ++c) {
     double W = (double)(max_width / c + 1);
+    if (c > 8 && W * (double)(1u << (c - 1)) * (double)ncols * (double)point_bytes > kMaxBucketBytes)
+      break;
     double cost = W * ((double)max_n + 2.5 * (double)(1u << (c - 1)));
     if (cost < best_cost) {
       best_cost = cost;
@@ -596,7 +602,8 @@ struct MsmPlan {
   std::vector<ColumnDesc> cols;  // first_window / num_windows filled in
 };
 
-inline MsmPlan msm_make_plan(std::vector<ColumnDesc> cols, const MsmOptions& opt) {
+inline MsmPlan msm_make_plan(std::vector<ColumnDesc> cols, const MsmOptions& opt,
+                             size_t point_bytes) {
   MsmPlan p;
   p.ncols = (u32)cols.size();
   u32 max_width = 1;
@@ -606,7 +613,8 @@ inline MsmPlan msm_make_plan(std::vector<ColumnDesc> cols, const MsmOptions& opt
     if (col.n)
       max_width = std::max(max_width, col.bit_width);
   }
-  p.c = opt.window_bits ? opt.window_bits : choose_window_bits(p.max_n, max_width);
+  p.c = opt.window_bits ? opt.window_bits
+                        : choose_window_bits(p.max_n, max_width, p.ncols, point_bytes);
   p.nbuckets = 1u << (p.c - 1);
   u64 max_entries = 0;
   for (auto& col : cols) {
@@ -805,7 +813,7 @@ void msm_run(stream_t s, const typename C::Gen* gens, std::vector<ColumnDesc> co
   typedef typename C::Point Point;
   if (cols.empty())
     return;
-  MsmPlan plan = msm_make_plan(std::move(cols), opt);
+  MsmPlan plan = msm_make_plan(std::move(cols), opt, sizeof(Point));
   if (plan.total_terms == 0 || plan.total_windows == 0) {
     if (hook)
       hook->before_range(0, plan.max_n);

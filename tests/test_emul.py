@@ -40,7 +40,7 @@ def test_random_ragged_signed_columns(emul, port, curve):
     assert common.same(curve, emul.commit(curve, cols, gens), port.commit(curve, cols, gens))
 
 
-@pytest.mark.parametrize("window_bits", [2, 3, 5, 7, 8, 11, 13, 16])
+@pytest.mark.parametrize("window_bits", [2, 3, 5, 7, 8, 11, 13, 16, 18, 20])
 def test_every_window_width(emul, port, window_bits):
     rng = np.random.default_rng(window_bits)
     n = 300

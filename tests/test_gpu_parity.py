@@ -96,7 +96,7 @@ def test_skewed_digits_and_tuning(bb, port):
     cols = [(ones, 0)] + common.random_columns(rng, n, [(0, 32, 0), (0, 4, 1)])
     want = port.commit(0, cols, gens)
     try:
-        for c, k1, kn in [(2, 32, 8), (5, 7, 5), (8, 64, 4), (11, 16, 16), (13, 32, 8), (16, 32, 8)]:
+        for c, k1, kn in [(2, 32, 8), (5, 7, 5), (8, 64, 4), (11, 16, 16), (13, 32, 8), (16, 32, 8), (19, 0, 8)]:
             bb.lib().b200_set_tuning(C.c_uint(c), C.c_uint(k1), C.c_uint(kn))
             assert np.array_equal(bb.compute_pedersen_commitments(0, cols, gens), want), (c, k1, kn)
     finally:
