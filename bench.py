@@ -56,7 +56,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
                  "-i", str(self.dev)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -265,7 +265,6 @@ def run_cuda(args, rank, local_rank, world):
     ms = e0.elapsed_ms(e1)
     barrier()
     launches = bb.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     acc_ms, acc_launches = bb.profile_read()
     bb.profile_accumulate(False)
     dev_result = d_out.cpu().numpy()[:32].copy()
@@ -280,6 +279,7 @@ def run_cuda(args, rank, local_rank, world):
     bb.synchronize()
     t_e2e = time.perf_counter() - t0
     barrier()
+    clocks = sampler.stop() if rank == 0 else None  # sampled across both timed regions
 
     if dist is not None:
         t = torch.tensor([ms, t_e2e], dtype=torch.float64, device="cuda")
