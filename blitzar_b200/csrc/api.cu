@@ -220,15 +220,15 @@ struct RangeWaitState {
   uint64_t n;
   uint32_t num_ranges;
 };
-void wait_for_range(void* user, uint64_t begin, uint64_t) {
+void wait_for_range(void* user, uint64_t begin, uint64_t end) {
   auto* st = static_cast<RangeWaitState*>(user);
-  for (uint32_t r = 0; r < st->num_ranges; ++r)
-    if (range_begin(st->n, r, st->num_ranges) == begin) {
+  // wait for every upload piece that intersects [begin, end) (column groups ask for all of them)
+  for (uint32_t r = 0; r < st->num_ranges; ++r) {
+    const uint64_t rb = range_begin(st->n, r, st->num_ranges);
+    const uint64_t re = range_begin(st->n, r + 1, st->num_ranges);
+    if (rb < end && begin < re)
       B200_CUDA(cudaStreamWaitEvent(g_state.stream, g_state.range_events[r], 0));
-      return;
-    }
-  // a range the copy schedule does not know (column groups): wait for everything
-  B200_CUDA(cudaStreamWaitEvent(g_state.stream, g_state.range_events[st->num_ranges - 1], 0));
+  }
 }
 
 void commit_host(unsigned curve_id, void* commitments, uint32_t num,
