@@ -36,7 +36,12 @@ struct State {
   MsmOptions opt;
 };
 State g_state;
-EngineCtx ctx() { return EngineCtx{g_state.stream, g_state.opt, g_state.builtin, g_state.num_builtin}; }
+EngineCtx ctx() {
+  EngineCtx c{g_state.stream, g_state.opt, g_state.builtin, g_state.num_builtin};
+  if (const char* env = std::getenv("BLITZAR_B200_GROUP_ENTRIES"))  // test hook: force column groups
+    c.opt.max_group_entries = std::strtoull(env, nullptr, 10);
+  return c;
+}
 std::mutex g_mutex;  // calls are serialised on the one library stream
 
 void ensure_device() {

@@ -38,7 +38,7 @@ template <class C> struct CurveOps {
   // sort scratch stays within a few GB of HBM.
   static void run_columns(const EngineCtx& ctx, const Gen* gens, std::vector<ColumnDesc>& cols,
                           Point* out, u32 num_ranges = 1, RangeHook* hook = nullptr) {
-    const uint64_t kMaxEntries = 1ull << 30;
+    const uint64_t kMaxEntries = ctx.opt.max_group_entries;
     size_t b = 0;
     while (b < cols.size()) {
       size_t e = b;

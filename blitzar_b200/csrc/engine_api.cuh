@@ -15,6 +15,7 @@ struct MsmOptions {
   u32 reduce_g1 = 16;   // bucket-reduction group size, first level (power of two)
   u32 reduce_gn = 4;    // bucket-reduction group size, later levels (power of two)
   u64 quad_threshold = 32768;  // launches with at most this many logical threads run 4 lanes each
+  u64 max_group_entries = 1ull << 30;  // columns are grouped below this many (term, window) entries
 };
 
 struct EngineCtx {

@@ -195,3 +195,20 @@ def test_full_size_properties_c2(bb, port):
     assert np.array_equal(got, port.commit(0, [(s[:m], 0)], gens[:m]))
     for b_ in (dg, ds, parts, out):
         b_.free()
+
+
+def test_upload_pieces_and_column_groups(bb, port, monkeypatch):
+    """Host calls upload the generator range in pieces (copy stream) while earlier pieces are being
+    accumulated; with several column groups every group must see all pieces."""
+    rng = np.random.default_rng(31)
+    n = 9000
+    gens, _ = common.generators_for(port, 0, n)
+    cols = common.random_columns(rng, n, [(0, 32, 0), (-4000, 16, 1), (0, 8, 0), (-8999, 32, 0)])
+    want = port.commit(0, cols, gens)
+    for ranges, group_entries in (("3", None), ("5", "50000"), ("1", "20000")):
+        monkeypatch.setenv("BLITZAR_B200_RANGES", ranges)
+        if group_entries:
+            monkeypatch.setenv("BLITZAR_B200_GROUP_ENTRIES", group_entries)
+        assert np.array_equal(bb.compute_pedersen_commitments(0, cols, gens), want), (ranges, group_entries)
+        assert np.array_equal(bb.compute_pedersen_commitments(0, cols[:2], None, 7),
+                              port.commit(0, cols[:2], None, 7))
