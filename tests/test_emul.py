@@ -157,3 +157,22 @@ def test_fp64_pipe_multiplication_is_exact(emul):
     """The (disabled, measured-not-faster) FP64-pipe multiplier keeps exact integer semantics."""
     import ctypes as C
     assert int(emul.lib().emul_check_fp64(C.c_uint(3000), C.c_uint(9))) == 0
+
+
+def test_column_groups_with_generator_ranges(emul, port):
+    """Several column groups (forced small) each make a full pass over generators that arrive in
+    pieces."""
+    rng = np.random.default_rng(12)
+    n = 400
+    gens, _ = common.generators_for(port, 0, n)
+    cols = common.random_columns(rng, n, [(0, 32, 0), (-100, 16, 1), (0, 8, 0), (-399, 32, 0), (0, 4, 0)])
+    try:
+        emul.set_ranges(3)
+        emul.set_group_entries(4000)
+        got = emul.commit(0, cols, gens)
+        got_builtin = emul.commit(0, cols, None, 9)
+    finally:
+        emul.set_ranges(1)
+        emul.set_group_entries(0)
+    assert common.same(0, got, port.commit(0, cols, gens))
+    assert common.same(0, got_builtin, port.commit(0, cols, None, 9))
