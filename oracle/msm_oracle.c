@@ -29,6 +29,8 @@
  *                   combination_kernel.h:81-106, combination.h:28-62), serial on one core.
  *   fixed-base      row-major scalar table, packed and variable-length variants:
  *                   cbindings/blitzar_api.h:663-744, sxt/multiexp/pippenger2/reduce.h:37-47.
+ *   inner product   prover / verifier, Merlin transcript and scalars mod l: see the banner above
+ *                   oracle_prove_inner_product (bottom of this file).
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -592,4 +594,229 @@ void oracle_test_points(unsigned curve, uint8_t* out_affine, uint8_t* out_proj, 
       memcpy(d, x.v, nb); memcpy(d + nb, y.v, nb); d[2 * nb] = (uint8_t)inf;
     }
   }
+}
+
+/* ================================================================================================
+ * Inner-product argument (restated from cbindings/inner_product_proof.cc:101-167,
+ * sxt/proof/inner_product/proof_computation.cc:61-155, cpu_driver.cc:47-257, fold.cc:28-49,
+ * verification_computation.cc:31-127) with its Merlin transcript (sxt/proof/transcript/
+ * strobe128.cc:47-160, transcript.cc:41-88, transcript_utility.cc:27-31, keccakf.cc) and the scalar
+ * field mod l (sxt/scalar25/operation/{mul,muladd,inv,reduce}.cc).
+ * ==============================================================================================*/
+typedef struct { u64 v[4]; } sc;
+static const u64 SC_L[4] = {0x5812631a5cf5d3edULL, 0x14def9dea2f79cd6ULL, 0ULL, 0x1000000000000000ULL};
+static u64 SC_INV, SC_R2[4];
+static int sc_ready = 0;
+static void sc_init(void) {
+  if (sc_ready) return;
+  u64 x = 1; for (int i = 0; i < 6; ++i) x *= 2 - SC_L[0] * x; SC_INV = (u64)0 - x;
+  u64 t[MAXN]; memset(t, 0, sizeof(t)); t[0] = 1;
+  for (int i = 0; i < 512; ++i) { u64 c = mf_addn(t, t, t, 4); if (c || mf_geq(t, SC_L, 4)) mf_subn(t, t, SC_L, 4); }
+  memcpy(SC_R2, t, 32); sc_ready = 1;
+}
+static void sc_mont(sc* r, const sc* a, const u64* b) {
+  u64 t[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; ++i) {
+    u128 c = 0;
+    for (int j = 0; j < 4; ++j) { c += (u128)a->v[j] * b[i] + t[j]; t[j] = (u64)c; c >>= 64; }
+    c += t[4]; t[4] = (u64)c; t[5] = (u64)(c >> 64);
+    u64 m = t[0] * SC_INV;
+    c = ((u128)m * SC_L[0] + t[0]) >> 64;
+    for (int j = 1; j < 4; ++j) { c += (u128)m * SC_L[j] + t[j]; t[j - 1] = (u64)c; c >>= 64; }
+    c += t[4]; t[3] = (u64)c; t[4] = t[5] + (u64)(c >> 64);
+  }
+  if (t[4] || mf_geq(t, SC_L, 4)) mf_subn(t, t, SC_L, 4);
+  memcpy(r->v, t, 32);
+}
+static sc sc_mul(sc a, sc b) { sc t, r; sc_mont(&t, &a, b.v); sc_mont(&r, &t, SC_R2); return r; }
+static sc sc_reduce32(sc a) { sc t, r; u64 one[4] = {1, 0, 0, 0}; sc_mont(&t, &a, SC_R2); sc_mont(&r, &t, one); return r; }
+static sc sc_add(sc a, sc b) { sc r; u64 c = mf_addn(r.v, a.v, b.v, 4); if (c || mf_geq(r.v, SC_L, 4)) mf_subn(r.v, r.v, SC_L, 4); return r; }
+static sc sc_sub(sc a, sc b) { sc r; if (mf_subn(r.v, a.v, b.v, 4)) mf_addn(r.v, r.v, SC_L, 4); return r; }
+static sc sc_neg(sc a) { sc z = {{0, 0, 0, 0}}; return sc_sub(z, a); }
+static sc sc_inv(sc a) {
+  u64 e[4], two[4] = {2, 0, 0, 0}; mf_subn(e, SC_L, two, 4);
+  sc acc = {{1, 0, 0, 0}};
+  for (int i = 255; i >= 0; --i) { acc = sc_mul(acc, acc); if ((e[i >> 6] >> (i & 63)) & 1) acc = sc_mul(acc, a); }
+  return acc;
+}
+static sc sc_load(const uint8_t* b) { sc r; memcpy(r.v, b, 32); return r; }
+static sc sc_inner(const uint8_t* a, const uint8_t* b, u64 n) {
+  sc acc = {{0, 0, 0, 0}};
+  for (u64 i = 0; i < n; ++i) acc = sc_add(acc, sc_mul(sc_load(a + 32 * i), sc_load(b + 32 * i)));
+  return acc;
+}
+
+/* Keccak-f[1600] (FIPS 202) */
+static u64 rotl64(u64 x, int s) { return (x << s) | (x >> (64 - s)); }
+static void keccakf(uint8_t* st) {
+  static const u64 RC[24] = {
+      0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL,
+      0x000000000000808bULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
+      0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
+      0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL,
+      0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
+      0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+  u64 a[25]; memcpy(a, st, 200);
+  for (int round = 0; round < 24; ++round) {
+    u64 c[5], b[25];
+    for (int x = 0; x < 5; ++x) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
+    for (int x = 0; x < 5; ++x) { u64 d = c[(x + 4) % 5] ^ rotl64(c[(x + 1) % 5], 1); for (int y = 0; y < 25; y += 5) a[y + x] ^= d; }
+    /* rho + pi from the definition: B[y][2x+3y] = rot(A[x][y], r[x][y]) */
+    static const int R[5][5] = {{0, 36, 3, 41, 18}, {1, 44, 10, 45, 2}, {62, 6, 43, 15, 61}, {28, 55, 25, 21, 56}, {27, 20, 39, 8, 14}};
+    for (int x = 0; x < 5; ++x) for (int y = 0; y < 5; ++y) {
+      int nx = y, ny = (2 * x + 3 * y) % 5;
+      u64 v = a[5 * y + x];
+      b[5 * ny + nx] = R[x][y] ? rotl64(v, R[x][y]) : v;
+    }
+    for (int y = 0; y < 5; ++y) for (int x = 0; x < 5; ++x) a[5 * y + x] = b[5 * y + x] ^ (~b[5 * y + (x + 1) % 5] & b[5 * y + (x + 2) % 5]);
+    a[0] ^= RC[round];
+  }
+  memcpy(st, a, 200);
+}
+/* STROBE-128 subset used by Merlin, on the 203-byte transcript {state[200], pos, pos_begin, cur_flags} */
+#define ST_R 166
+static void st_run_f(uint8_t* s) { s[s[200]] ^= s[201]; s[s[200] + 1] ^= 0x04; s[ST_R + 1] ^= 0x80; keccakf(s); s[200] = 0; s[201] = 0; }
+static void st_absorb(uint8_t* s, const uint8_t* d, size_t n) { for (size_t i = 0; i < n; ++i) { s[s[200]] ^= d[i]; s[200] += 1; if (s[200] == ST_R) st_run_f(s); } }
+static void st_squeeze(uint8_t* s, uint8_t* d, size_t n) { for (size_t i = 0; i < n; ++i) { d[i] = s[s[200]]; s[s[200]] = 0; s[200] += 1; if (s[200] == ST_R) st_run_f(s); } }
+static void st_begin(uint8_t* s, uint8_t flags, int more) {
+  if (more) return;
+  uint8_t old = s[201]; s[201] = (uint8_t)(s[200] + 1); s[202] = flags;
+  uint8_t d[2] = {old, flags}; st_absorb(s, d, 2);
+  if ((flags & (4 | 32)) && s[200] != 0) st_run_f(s);
+}
+static void st_meta_ad(uint8_t* s, const uint8_t* d, size_t n, int more) { st_begin(s, 16 | 2, more); st_absorb(s, d, n); }
+static void tr_append(uint8_t* s, const char* label, const uint8_t* msg, size_t n) {
+  uint32_t len = (uint32_t)n;
+  st_meta_ad(s, (const uint8_t*)label, strlen(label), 0); st_meta_ad(s, (const uint8_t*)&len, 4, 1);
+  st_begin(s, 2, 0); st_absorb(s, msg, n);
+}
+static void tr_challenge(uint8_t* s, uint8_t* out, size_t n, const char* label) {
+  uint32_t len = (uint32_t)n;
+  st_meta_ad(s, (const uint8_t*)label, strlen(label), 0); st_meta_ad(s, (const uint8_t*)&len, 4, 1);
+  st_begin(s, 1 | 2 | 4, 0); st_squeeze(s, out, n);
+}
+void oracle_transcript_new(uint8_t* t203, const char* label) {
+  static const uint8_t init[19] = {1, 168, 1, 0, 1, 96, 83, 84, 82, 79, 66, 69, 118, 49, 46, 48, 46, 50, 0};
+  memset(t203, 0, 203); memcpy(t203, init, 19);
+  keccakf(t203);
+  st_meta_ad(t203, (const uint8_t*)"Merlin v1.0", 11, 0);
+  tr_append(t203, "dom-sep", (const uint8_t*)label, strlen(label));
+}
+static sc ipa_challenge(uint8_t* t, const uint8_t* l32, const uint8_t* r32) {
+  tr_append(t, "L", l32, 32); tr_append(t, "R", r32, 32);
+  uint8_t buf[32]; tr_challenge(t, buf, 32, "x");
+  return sc_reduce32(sc_load(buf));
+}
+static void ipa_init(uint8_t* t, u64 n) {
+  const char* dom = "inner product proof v1";
+  tr_append(t, "domain-sep", (const uint8_t*)dom, strlen(dom)); tr_append(t, "n", (const uint8_t*)&n, 8);
+}
+static void ge_scalarmult(ge* r, const ge* p, const sc* k) {
+  ge acc; ge_identity(&acc);
+  for (int i = 255; i >= 0; --i) { ge_dbl(&acc, &acc); if ((k->v[i >> 6] >> (i & 63)) & 1) ge_add(&acc, &acc, p); }
+  *r = acc;
+}
+/* sum_i s_i * g_i with 32-byte scalars (naive double-and-add: the oracle favours obviousness) */
+static void ge_msm(ge* r, const ge* g, const uint8_t* scalars, u64 n) {
+  ge acc; ge_identity(&acc);
+  for (u64 i = 0; i < n; ++i) { sc k = sc_load(scalars + 32 * i); ge t; ge_scalarmult(&t, &g[i], &k); ge_add(&acc, &acc, &t); }
+  *r = acc;
+}
+static unsigned ipa_log2(u64 n) { unsigned k = 0; while ((1ull << k) < n) ++k; return k; }
+
+void oracle_prove_inner_product(uint8_t* l_vector, uint8_t* r_vector, uint8_t* ap_value, uint8_t* t203,
+                                u64 n, u64 generators_offset, const uint8_t* a_vector, const uint8_t* b_vector) {
+  oracle_init(); sc_init();
+  unsigned k = ipa_log2(n); u64 np = 1ull << k;
+  ipa_init(t203, n);
+  if (n == 1) { memcpy(ap_value, a_vector, 32); return; }
+  ge* G = (ge*)malloc(sizeof(ge) * (np + 1));
+  for (u64 i = 0; i <= np; ++i) builtin_generator(&G[i], generators_offset + i);
+  ge Q = G[np];
+  uint8_t* a = (uint8_t*)malloc(32 * np); uint8_t* b = (uint8_t*)malloc(32 * np);
+  memcpy(a, a_vector, 32 * n); memcpy(b, b_vector, 32 * n);
+  u64 na = n, nb = n, len = np;
+  for (unsigned round = 0; round < k; ++round) {
+    u64 mid = len / 2, a_hi = na - mid, b_hi = nb - mid;
+    sc c_l = sc_inner(a, b + 32 * mid, mid < b_hi ? mid : b_hi);
+    sc c_r = sc_inner(a + 32 * mid, b, a_hi < mid ? a_hi : mid);
+    ge L, R, t;
+    ge_msm(&L, G + mid, a, mid); ge_scalarmult(&t, &Q, &c_l); ge_add(&L, &L, &t);
+    ge_msm(&R, G, a + 32 * mid, a_hi); ge_scalarmult(&t, &Q, &c_r); ge_add(&R, &R, &t);
+    ristretto_encode(l_vector + 32 * round, &L); ristretto_encode(r_vector + 32 * round, &R);
+    sc x = ipa_challenge(t203, l_vector + 32 * round, r_vector + 32 * round), xi = sc_inv(x);
+    for (u64 i = 0; i < mid; ++i) { /* a' = x a_lo + x^-1 a_hi (zero padded) */
+      sc v = sc_mul(x, sc_load(a + 32 * i));
+      if (i < a_hi) v = sc_add(v, sc_mul(xi, sc_load(a + 32 * (mid + i))));
+      memcpy(a + 32 * i, v.v, 32);
+    }
+    na = mid;
+    if (mid == 1) break;
+    for (u64 i = 0; i < mid; ++i) { /* b' = x^-1 b_lo + x b_hi */
+      sc v = sc_mul(xi, sc_load(b + 32 * i));
+      if (i < b_hi) v = sc_add(v, sc_mul(x, sc_load(b + 32 * (mid + i))));
+      memcpy(b + 32 * i, v.v, 32);
+    }
+    nb = mid;
+    for (u64 i = 0; i < mid; ++i) { /* G' = x^-1 G_lo + x G_hi */
+      ge lo, hi; ge_scalarmult(&lo, &G[i], &xi); ge_scalarmult(&hi, &G[mid + i], &x); ge_add(&G[i], &lo, &hi);
+    }
+    len = mid;
+  }
+  memcpy(ap_value, a, 32);
+  free(G); free(a); free(b);
+}
+
+/* ristretto255 decoding (RFC 9496 4.3.1; sxt/ristretto/base/byte_conversion.cc:135-) */
+static int ristretto_decode(ge* p, const uint8_t* bytes) {
+  fe s, ss, u1, u2, u2sq, v, t, inv_sqrt, den_x, den_y;
+  uint8_t back[32];
+  fe_frombytes(&s, bytes); fe_tobytes(back, &s);
+  if (memcmp(back, bytes, 32) != 0 || (bytes[0] & 1)) return 0;
+  fe_sq(&ss, &s); fe_sub(&u1, &FE_ONE, &ss); fe_add(&u2, &FE_ONE, &ss); fe_sq(&u2sq, &u2);
+  fe_sq(&t, &u1); fe_mul(&t, &t, &FE_D); fe_neg(&v, &t); fe_sub(&v, &v, &u2sq);
+  fe_mul(&t, &v, &u2sq);
+  int was_square = sqrt_ratio_m1(&inv_sqrt, &FE_ONE, &t);
+  fe_mul(&den_x, &inv_sqrt, &u2); fe_mul(&den_y, &inv_sqrt, &den_x); fe_mul(&den_y, &den_y, &v);
+  fe_mul(&p->X, &s, &den_x); fe_add(&p->X, &p->X, &p->X); fe_abs(&p->X, &p->X);
+  fe_mul(&p->Y, &u1, &den_y); p->Z = FE_ONE; fe_mul(&p->T, &p->X, &p->Y);
+  return was_square && !fe_isneg(&p->T) && !fe_iszero(&p->Y);
+}
+
+int oracle_verify_inner_product(uint8_t* t203, u64 n, u64 generators_offset, const uint8_t* b_vector,
+                                const uint8_t* product, const uint8_t* a_commit160, const uint8_t* l_vector,
+                                const uint8_t* r_vector, const uint8_t* ap_value) {
+  oracle_init(); sc_init();
+  unsigned k = ipa_log2(n); u64 np = 1ull << k;
+  ipa_init(t203, n);
+  sc* x = (sc*)malloc(sizeof(sc) * (k ? k : 1));
+  for (unsigned j = 0; j < k; ++j) x[j] = ipa_challenge(t203, l_vector + 32 * j, r_vector + 32 * j);
+  ge* G = (ge*)malloc(sizeof(ge) * (np + 1));
+  for (u64 i = 0; i <= np; ++i) builtin_generator(&G[i], generators_offset + i);
+  /* s_i = ap * prod_j x_j^(+-1), bit t of i <-> x_{k-1-t} */
+  sc ap = sc_load(ap_value), allinv = {{1, 0, 0, 0}};
+  for (unsigned j = 0; j < k; ++j) allinv = sc_mul(allinv, sc_inv(x[j]));
+  sc* g = (sc*)malloc(sizeof(sc) * np);
+  g[0] = sc_mul(allinv, ap);
+  u64 filled = 1;
+  for (unsigned t = 0; t < k; ++t) { sc m = sc_mul(x[k - 1 - t], x[k - 1 - t]); for (u64 i = 0; i < filled; ++i) g[filled + i] = sc_mul(m, g[i]); filled *= 2; }
+  sc prod = {{0, 0, 0, 0}};
+  for (u64 i = 0; i < n; ++i) prod = sc_add(prod, sc_mul(g[i], sc_load(b_vector + 32 * i)));
+  ge expected, t; ge_scalarmult(&expected, &G[np], &prod);
+  for (u64 i = 0; i < np; ++i) { ge_scalarmult(&t, &G[i], &g[i]); ge_add(&expected, &expected, &t); }
+  int ok = 1;
+  for (unsigned j = 0; j < k; ++j) {
+    ge Lp, Rp; sc xi = sc_inv(x[j]);
+    sc el = sc_neg(sc_mul(x[j], x[j])), er = sc_neg(sc_mul(xi, xi));
+    ok &= ristretto_decode(&Lp, l_vector + 32 * j); ok &= ristretto_decode(&Rp, r_vector + 32 * j);
+    if (!ok) break;
+    ge_scalarmult(&t, &Lp, &el); ge_add(&expected, &expected, &t);
+    ge_scalarmult(&t, &Rp, &er); ge_add(&expected, &expected, &t);
+  }
+  ge commit, A; sc pr = sc_load(product);
+  memcpy(&A, a_commit160, 160);
+  ge_scalarmult(&commit, &G[np], &pr); ge_add(&commit, &commit, &A);
+  uint8_t e1[32], e2[32]; ristretto_encode(e1, &expected); ristretto_encode(e2, &commit);
+  free(x); free(G); free(g);
+  return ok && memcmp(e1, e2, 32) == 0;
 }

@@ -98,3 +98,39 @@ def fixed_msm(curve_id, generators_p, num_outputs, n, scalars, element_num_bytes
                            C.c_int(mode), C.c_uint(element_num_bytes), bt, ol,
                            C.c_uint(num_outputs), C.c_uint(n), C.c_void_p(scalars.ctypes.data))
     return res
+
+
+# ---- inner-product argument ---------------------------------------------------------------------
+def transcript_new(label=b"ip-test"):
+    t = np.zeros(203, dtype=np.uint8)
+    lib().oracle_transcript_new(C.c_void_p(t.ctypes.data), C.c_char_p(label))
+    return t
+
+
+def prove_inner_product(transcript, a, b, generators_offset=0):
+    n = a.shape[0]
+    rounds = max(0, (n - 1).bit_length())
+    lv = np.zeros((max(rounds, 1), 32), dtype=np.uint8)
+    rv = np.zeros((max(rounds, 1), 32), dtype=np.uint8)
+    ap = np.zeros(32, dtype=np.uint8)
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    b = np.ascontiguousarray(b, dtype=np.uint8)
+    lib().oracle_prove_inner_product(C.c_void_p(lv.ctypes.data), C.c_void_p(rv.ctypes.data),
+                                     C.c_void_p(ap.ctypes.data), C.c_void_p(transcript.ctypes.data),
+                                     C.c_uint64(n), C.c_uint64(generators_offset),
+                                     C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data))
+    return lv[:rounds], rv[:rounds], ap
+
+
+def verify_inner_product(transcript, b, product, a_commit, l_vector, r_vector, ap_value,
+                         generators_offset=0):
+    n = b.shape[0]
+    b = np.ascontiguousarray(b, dtype=np.uint8)
+    lv = np.ascontiguousarray(l_vector if len(l_vector) else np.zeros((1, 32), np.uint8))
+    rv = np.ascontiguousarray(r_vector if len(r_vector) else np.zeros((1, 32), np.uint8))
+    lib().oracle_verify_inner_product.restype = C.c_int
+    return int(lib().oracle_verify_inner_product(
+        C.c_void_p(transcript.ctypes.data), C.c_uint64(n), C.c_uint64(generators_offset),
+        C.c_void_p(b.ctypes.data), C.c_void_p(np.ascontiguousarray(product).ctypes.data),
+        C.c_void_p(np.ascontiguousarray(a_commit).ctypes.data), C.c_void_p(lv.ctypes.data),
+        C.c_void_p(rv.ctypes.data), C.c_void_p(np.ascontiguousarray(ap_value).ctypes.data)))

@@ -2,8 +2,7 @@
 reference's cpu backend — committed fixtures generated from oracle/_ref (tests/golden/
 inner_product.npz, script make_golden.py) and, when oracle/_ref is present, live random cases.
 Mirrors cbindings/inner_product_proof.t.cc (prove then verify, tampered inputs are rejected).
-The C port of the oracle does not restate this part: parity for it is pinned on the reference's own
-implementation only."""
+The C port of the oracle restates the protocol too and is pinned on the same fixtures."""
 import os
 
 import numpy as np
@@ -39,8 +38,41 @@ def _check_against_fixture(engine):
                                                z[f"acommit{ci}"], lbad, rv, ap, off) == 0, ci
 
 
+def test_oracle_port_matches_reference_fixture(port):
+    _check_against_fixture(port)
+
+
+def test_oracle_port_matches_reference_live(port, refcpu):
+    rng = np.random.default_rng(15)
+    for n in (1, 2, 7, 12):
+        av = [int.from_bytes(rng.bytes(32), "little") % L for _ in range(n)]
+        bv = [int.from_bytes(rng.bytes(32), "little") % L for _ in range(n)]
+        a = np.array([list(v.to_bytes(32, "little")) for v in av], dtype=np.uint8)
+        b = np.array([list(v.to_bytes(32, "little")) for v in bv], dtype=np.uint8)
+        assert np.array_equal(port.transcript_new(b"xyz"), refcpu.transcript_new(b"xyz"))
+        t_ref = refcpu.transcript_new(b"live")
+        t = t_ref.copy()
+        want = refcpu.prove_inner_product(t_ref, a, b, 4)
+        got = port.prove_inner_product(t, a, b, 4)
+        assert all(np.array_equal(x, y) for x, y in zip(want, got)) and np.array_equal(t, t_ref)
+
+
 def test_emulated_pipeline_matches_reference_fixture(emul):
     _check_against_fixture(emul)
+
+
+def test_emulated_pipeline_matches_oracle_port_live(emul, port):
+    rng = np.random.default_rng(25)
+    for n in (4, 9, 33):
+        a = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        b = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        a[:, 31] &= 0x0F
+        b[:, 31] &= 0x0F
+        t0 = port.transcript_new(b"emul-live")
+        t1, t2 = t0.copy(), t0.copy()
+        want = port.prove_inner_product(t1, a, b, 1)
+        got = emul.prove_inner_product(t2, a, b, 1)
+        assert all(np.array_equal(x, y) for x, y in zip(want, got)) and np.array_equal(t1, t2)
 
 
 def test_emulated_pipeline_matches_reference_live(emul, refcpu):
@@ -60,6 +92,21 @@ def test_emulated_pipeline_matches_reference_live(emul, refcpu):
 @pytest.mark.gpu
 def test_gpu_matches_reference_fixture(bb):
     _check_against_fixture(bb)
+
+
+@pytest.mark.gpu
+def test_gpu_matches_oracle_port_live(bb, port):
+    rng = np.random.default_rng(35)
+    for n in (6, 50, 300):
+        a = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        b = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        a[:, 31] &= 0x0F
+        b[:, 31] &= 0x0F
+        t0 = port.transcript_new(b"gpu-live")
+        t1, t2 = t0.copy(), t0.copy()
+        want = port.prove_inner_product(t1, a, b, 70)  # straddles the 64 precomputed generators
+        got = bb.prove_inner_product(t2, a, b, 70)
+        assert all(np.array_equal(x, y) for x, y in zip(want, got)) and np.array_equal(t1, t2)
 
 
 @pytest.mark.gpu
