@@ -140,7 +140,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_sample = 1 << 15
+    n_sample = 1 << 14  # per process and step: keeps a 20-step run within ~2 minutes on a 200-core host
     from oracle import refcpu
     use_ref = refcpu.available()
     kind = "reference" if use_ref else "port"
@@ -155,7 +155,7 @@ def run_reference(args, rank, world):
                                                for i in range(cores)]))
     terms = args.steps * cores * n_sample
     value = terms / wall
-    sample = (f"{cores} concurrent single-threaded MSMs of n=2^15 ristretto terms per step "
+    sample = (f"{cores} concurrent single-threaded MSMs of n=2^14 ristretto terms per step "
               f"(the workload's 2^20-term column is out of reach of a bounded CPU run; the "
               f"reference cpu backend is serial per call)")
     line = {
