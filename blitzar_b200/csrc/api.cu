@@ -112,7 +112,11 @@ public:
     bool pinned = cudaPointerGetAttributes(&attr, src_host) == cudaSuccess &&
                   (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
     cudaGetLastError();  // unregistered host memory may set a sticky-free error on old drivers
-    if (pinned || bytes < (1u << 20)) {
+    static const bool enabled = [] {
+      const char* env = std::getenv("BLITZAR_B200_STAGER");
+      return env == nullptr || std::atoi(env) != 0;  // on by default; BLITZAR_B200_STAGER=0 disables
+    }();
+    if (!enabled || pinned || bytes < (1u << 20)) {
       B200_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, sc));
       return;
     }
