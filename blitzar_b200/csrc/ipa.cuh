@@ -124,10 +124,11 @@ struct Ipa {
                                            const Sc& m_hi, uint64_t mid) {
     const uint64_t len = v.size() / 32, p = len - mid;
     std::vector<uint8_t> r(32 * mid);
+    const Sc lo_m = sc_to_mont(m_lo), hi_m = sc_to_mont(m_hi);  // one Montgomery product per term
     for (uint64_t i = 0; i < mid; ++i) {
-      Sc t = sc_mul(m_lo, sc_load(&v[32 * i]));
+      Sc t = sc_mul_mont(lo_m, sc_load(&v[32 * i]));
       if (i < p)
-        t = sc_muladd(m_hi, sc_load(&v[32 * (mid + i)]), t);
+        t = sc_add(t, sc_mul_mont(hi_m, sc_load(&v[32 * (mid + i)])));
       sc_store(&r[32 * i], t);
     }
     return r;
@@ -227,9 +228,9 @@ struct Ipa {
       g[0] = sc_mul(allinv, ap);
       uint64_t filled = 1;
       for (unsigned t = 0; t < k; ++t) {
-        const Sc& m = xsq[k - 1 - t];
+        const Sc m = sc_to_mont(xsq[k - 1 - t]);
         for (uint64_t i = 0; i < filled; ++i)
-          g[filled + i] = sc_mul(m, g[i]);
+          g[filled + i] = sc_mul_mont(m, g[i]);
         filled *= 2;
       }
       Sc prod = sc_zero();

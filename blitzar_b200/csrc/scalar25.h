@@ -120,6 +120,19 @@ inline Sc sc_mul(const Sc& a, const Sc& b) {
   mont_mul(r.v, t.v, consts().r2);  // a b
   return r;
 }
+// Montgomery form x*R of a canonical x; sc_mul_mont(xm, y) = x*y with ONE Montgomery product
+inline Sc sc_to_mont(const Sc& a) {
+  using namespace sc_detail;
+  Sc r;
+  mont_mul(r.v, a.v, consts().r2);
+  return r;
+}
+inline Sc sc_mul_mont(const Sc& a_mont, const Sc& b) {
+  using namespace sc_detail;
+  Sc r;
+  mont_mul(r.v, a_mont.v, b.v);
+  return r;
+}
 inline Sc sc_add(const Sc& a, const Sc& b) {
   using namespace sc_detail;
   Sc r;
