@@ -16,6 +16,8 @@ struct MsmOptions {
   u32 reduce_gn = 4;    // bucket-reduction group size, later levels (power of two)
   u64 quad_threshold = 32768;  // launches with at most this many logical threads run 4 lanes each
   u64 max_group_entries = 1ull << 30;  // columns are grouped below this many (term, window) entries
+  u64 max_range_entries = 1ull << 31;  // one sort pass holds at most this many entries: longer
+                                       // columns are processed as several generator ranges
 };
 
 struct EngineCtx {

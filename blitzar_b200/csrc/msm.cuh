@@ -599,7 +599,7 @@ inline u32 choose_window_bits(u64 max_n, u32 max_width, u32 ncols, size_t point_
 // of the same pass share one bucket array.
 struct MsmPlan {
   u32 c = 0, nbuckets = 0, ncols = 0, total_windows = 0;
-  u64 nkeys = 0, max_n = 0, total_terms = 0;
+  u64 nkeys = 0, max_n = 0, total_terms = 0, total_entries = 0;
   std::vector<ColumnDesc> cols;  // first_window / num_windows filled in
 };
 
@@ -625,7 +625,7 @@ inline MsmPlan msm_make_plan(std::vector<ColumnDesc> cols, const MsmOptions& opt
     max_entries += (u64)col.n * col.num_windows;
   }
   p.nkeys = (u64)p.total_windows * p.nbuckets;
-  B200_REQUIRE(max_entries < (1ull << 32), "too many (term, window) entries for one pass");
+  p.total_entries = max_entries;
   B200_REQUIRE(p.nkeys < (1ull << 32), "too many buckets for one pass");
   p.cols = std::move(cols);
   return p;
@@ -653,6 +653,8 @@ void msm_accumulate_range(stream_t s, const MsmPlan& plan, const typename C::Gen
   const u64 total_terms = col_start[ncols];
   if (total_terms == 0)
     return;
+  B200_REQUIRE(max_entries < (1ull << 32) && end - begin < (1ull << 31),
+               "too many (term, window) entries for one sort pass");
   const u32 c = plan.c, nbuckets = plan.nbuckets;
   const u64 nkeys = plan.nkeys;
   gens += begin;  // entry indices are relative to the range
@@ -827,6 +829,11 @@ void msm_run(stream_t s, const typename C::Gen* gens, std::vector<ColumnDesc> co
   dev_zero(d_window_used, plan.total_windows * sizeof(u32), s);
   if (num_ranges < 1)
     num_ranges = 1;
+  // very long columns: enough ranges that each sort pass stays below the entry limit
+  const u64 limit = opt.max_range_entries ? opt.max_range_entries : (1ull << 31);
+  const u64 needed = (plan.total_entries + limit - 1) / limit;
+  if (needed > num_ranges)
+    num_ranges = (u32)std::min<u64>(needed, plan.max_n);
   for (u32 r = 0; r < num_ranges; ++r) {
     u64 begin = range_begin(plan.max_n, r, num_ranges), end = range_begin(plan.max_n, r + 1, num_ranges);
     if (hook)

@@ -30,6 +30,7 @@ static unsigned g_ranges = 1;
 
 extern "C" {
 void emul_set_ranges(unsigned num_ranges) { g_ranges = num_ranges ? num_ranges : 1; }
+void emul_set_range_entries(unsigned long long v) { g_opt.max_range_entries = v ? v : (1ull << 31); }
 void emul_set_group_entries(unsigned long long v) { g_opt.max_group_entries = v ? v : (1ull << 30); }
 void emul_set_tuning(unsigned window_bits, unsigned chunk1, unsigned chunkn) {
   g_opt.window_bits = window_bits;

@@ -59,6 +59,10 @@ def set_tuning(window_bits=0, chunk1=0, chunkn=0):
     lib().emul_set_tuning(C.c_uint(window_bits), C.c_uint(chunk1), C.c_uint(chunkn))
 
 
+def set_range_entries(v=0):
+    lib().emul_set_range_entries(C.c_ulonglong(v))
+
+
 def set_group_entries(v=0):
     lib().emul_set_group_entries(C.c_ulonglong(v))
 

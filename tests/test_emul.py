@@ -176,3 +176,18 @@ def test_column_groups_with_generator_ranges(emul, port):
         emul.set_group_entries(0)
     assert common.same(0, got, port.commit(0, cols, gens))
     assert common.same(0, got_builtin, port.commit(0, cols, None, 9))
+
+
+def test_long_columns_split_into_sort_passes(emul, port):
+    """A column whose (term, window) entries exceed one sort pass is processed as several generator
+    ranges automatically (limit forced small here; 2^31 in production)."""
+    rng = np.random.default_rng(13)
+    n = 600
+    gens, _ = common.generators_for(port, 2, n)
+    cols = common.random_columns(rng, n, [(0, 32, 0), (-250, 8, 1)])
+    try:
+        emul.set_range_entries(3000)
+        got = emul.commit(2, cols, gens)
+    finally:
+        emul.set_range_entries(0)
+    assert common.same(2, got, port.commit(2, cols, gens))
