@@ -285,7 +285,8 @@ template <class C, class X> struct GatherAcc<C, X, true> {
 // keys stay sorted) for the next, K/2-times smaller, level. The final level writes everything.
 template <class C, bool kGather, class X = SeqExec> struct AccumulateBody {
   static constexpr int kBlock = 128;
-  static constexpr int kMinBlocks = kGather ? 3 : 1;  // cap registers at 168: 12 warps per SM
+  // register cap: 168 (3 blocks/SM) for 8-limb fields; 12-limb bls12-381 keeps 255 (2 blocks/SM)
+  static constexpr int kMinBlocks = !kGather ? 1 : (C::F::N > 8 ? 2 : 3);
   typedef typename C::Point Point;
   const u32* keys;                 // level >= 2
   const u64* entries;              // level 1: (key << 32) | (generator index << 1) | negate
