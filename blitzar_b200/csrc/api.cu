@@ -15,6 +15,7 @@
 #include <functional>
 #include <mutex>
 #include <thread>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -35,14 +36,28 @@ struct State {
   uint64_t num_builtin = 0;
   MsmOptions opt;
 };
-State g_state;
-EngineCtx ctx() {
-  EngineCtx c{g_state.stream, g_state.opt, g_state.builtin, g_state.num_builtin};
+State g_state;  // the primary device: every entry point runs here
+EngineCtx ctx_of(const State& st) {
+  EngineCtx c{st.stream, g_state.opt, st.builtin, st.num_builtin};
   if (const char* env = std::getenv("BLITZAR_B200_GROUP_ENTRIES"))  // test hook: force column groups
     c.opt.max_group_entries = std::strtoull(env, nullptr, 10);
   return c;
 }
+EngineCtx ctx() { return ctx_of(g_state); }
 std::mutex g_mutex;  // calls are serialised on the one library stream
+
+void init_device_state(State& st) {
+  B200_CUDA(cudaSetDevice(st.device));
+  B200_CUDA(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
+  B200_CUDA(cudaStreamCreateWithFlags(&st.copy_stream, cudaStreamNonBlocking));
+  for (auto& e : st.range_events)
+    B200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  B200_CUDA(cudaEventCreateWithFlags(&st.alloc_event, cudaEventDisableTiming));
+  cudaMemPool_t pool;
+  B200_CUDA(cudaDeviceGetDefaultMemPool(&pool, st.device));
+  uint64_t threshold = UINT64_MAX;  // keep freed blocks cached in the pool between calls
+  B200_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+}
 
 void ensure_device() {
   if (g_state.stream)
@@ -58,16 +73,7 @@ void ensure_device() {
     else
       B200_CUDA(cudaGetDevice(&g_state.device));
   }
-  B200_CUDA(cudaSetDevice(g_state.device));
-  B200_CUDA(cudaStreamCreateWithFlags(&g_state.stream, cudaStreamNonBlocking));
-  B200_CUDA(cudaStreamCreateWithFlags(&g_state.copy_stream, cudaStreamNonBlocking));
-  for (auto& e : g_state.range_events)
-    B200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  B200_CUDA(cudaEventCreateWithFlags(&g_state.alloc_event, cudaEventDisableTiming));
-  cudaMemPool_t pool;
-  B200_CUDA(cudaDeviceGetDefaultMemPool(&pool, g_state.device));
-  uint64_t threshold = UINT64_MAX;  // keep freed blocks cached in the pool between calls
-  B200_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+  init_device_state(g_state);
 }
 
 void require_init(const char* fn) {
@@ -102,7 +108,7 @@ const CurveVTable& vt(unsigned curve_id) {
 class HostStager {
 public:
   static HostStager& get() {
-    static HostStager s;
+    static thread_local HostStager s;  // one staging ring + pool per host thread (= per device)
     return s;
   }
   void copy(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t sc) {
@@ -228,31 +234,26 @@ uint64_t longest_column(const sxt_sequence_descriptor* d, uint32_t num) {
 struct RangeWaitState {
   uint64_t n;
   uint32_t num_ranges;
+  const State* st;
 };
 void wait_for_range(void* user, uint64_t begin, uint64_t end) {
-  auto* st = static_cast<RangeWaitState*>(user);
+  auto* w = static_cast<RangeWaitState*>(user);
   // wait for every upload piece that intersects [begin, end) (column groups ask for all of them)
-  for (uint32_t r = 0; r < st->num_ranges; ++r) {
-    const uint64_t rb = range_begin(st->n, r, st->num_ranges);
-    const uint64_t re = range_begin(st->n, r + 1, st->num_ranges);
+  for (uint32_t r = 0; r < w->num_ranges; ++r) {
+    const uint64_t rb = range_begin(w->n, r, w->num_ranges);
+    const uint64_t re = range_begin(w->n, r + 1, w->num_ranges);
     if (rb < end && begin < re)
-      B200_CUDA(cudaStreamWaitEvent(g_state.stream, g_state.range_events[r], 0));
+      B200_CUDA(cudaStreamWaitEvent(w->st->stream, w->st->range_events[r], 0));
   }
 }
 
-void commit_host(unsigned curve_id, void* commitments, uint32_t num,
-                 const sxt_sequence_descriptor* d, const void* generators,
-                 uint64_t offset_generators, const char* fn) {
-  if (num == 0)
-    return;
-  std::lock_guard<std::mutex> lock(g_mutex);
-  require_init(fn);
-  B200_REQUIRE(commitments != nullptr, "commitments == nullptr");
+// the commitments of `num` columns on one device (the calling thread's current device is st.device)
+void commit_on(const State& st, unsigned curve_id, void* commitments, uint32_t num,
+               const sxt_sequence_descriptor* d, const void* generators,
+               uint64_t offset_generators) {
   const CurveVTable& V = vt(curve_id);
-  cudaStream_t s = g_state.stream, sc = g_state.copy_stream;
+  cudaStream_t s = st.stream, sc = st.copy_stream;
   uint64_t n = longest_column(d, num);
-  if (curve_id != SXT_CURVE_RISTRETTO255)
-    B200_REQUIRE(generators != nullptr, "generators == nullptr");
   size_t total_scalar_bytes = 0;
   for (uint32_t i = 0; i < num; ++i)
     total_scalar_bytes += (size_t)d[i].n * d[i].element_nbytes + 32;
@@ -276,8 +277,8 @@ void commit_host(unsigned curve_id, void* commitments, uint32_t num,
   if (const char* env = std::getenv("BLITZAR_B200_RANGES"))
     num_ranges = (uint32_t)std::max(1, std::min(16, std::atoi(env)));
   // the destination buffers are stream-ordered allocations of the compute stream
-  B200_CUDA(cudaEventRecord(g_state.alloc_event, s));
-  B200_CUDA(cudaStreamWaitEvent(sc, g_state.alloc_event, 0));
+  B200_CUDA(cudaEventRecord(st.alloc_event, s));
+  B200_CUDA(cudaStreamWaitEvent(sc, st.alloc_event, 0));
   for (uint32_t r = 0; r < num_ranges; ++r) {
     const uint64_t b = range_begin(n, r, num_ranges), e = range_begin(n, r + 1, num_ranges);
     for (uint32_t i = 0; i < num; ++i) {
@@ -290,13 +291,118 @@ void commit_host(unsigned curve_id, void* commitments, uint32_t num,
       HostStager::get().copy(raw_gens.p + b * V.abi_gen_bytes,
                              static_cast<const unsigned char*>(generators) + b * V.abi_gen_bytes,
                              (e - b) * V.abi_gen_bytes, sc);
-    B200_CUDA(cudaEventRecord(g_state.range_events[r], sc));
+    B200_CUDA(cudaEventRecord(st.range_events[r], sc));
   }
-  RangeWaitState st{n, num_ranges};
-  V.commit_device(ctx(), out.p, nullptr, num, dd.data(), generators ? raw_gens.p : nullptr,
-                  offset_generators, num_ranges, &wait_for_range, &st);
+  RangeWaitState w{n, num_ranges, &st};
+  V.commit_device(ctx_of(st), out.p, nullptr, num, dd.data(), generators ? raw_gens.p : nullptr,
+                  offset_generators, num_ranges, &wait_for_range, &w);
   copy_d2h(commitments, out.p, (size_t)num * V.abi_commit_bytes, s);
   stream_sync(s);
+}
+
+// ---- optional in-process multi-GPU (BLITZAR_B200_DEVICES=k): independent columns are split over k
+// devices, one persistent host thread per extra device, no inter-GPU traffic (SURVEY §8e "by column";
+// the reference does the same with one host thread and round-robin cudaSetDevice,
+// sxt/execution/device/for_each.cc:57-126). Off by default: under one-process-per-GPU launchers
+// every rank already owns its device.
+class Worker {
+public:
+  State st;
+  explicit Worker(int device) {
+    st.device = device;
+    th_ = std::thread([this] { run(); });
+  }
+  void submit(std::function<void()> f) {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      task_ = std::move(f);
+      busy_ = true;
+    }
+    cv_.notify_all();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> lk(m_);
+    cv_.wait(lk, [this] { return !busy_; });
+  }
+  ~Worker() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    if (th_.joinable())
+      th_.join();
+  }
+
+private:
+  std::thread th_;
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::function<void()> task_;
+  bool busy_ = false, stop_ = false;
+  void run() {
+    B200_CUDA(cudaSetDevice(st.device));
+    for (;;) {
+      std::function<void()> f;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [this] { return stop_ || task_; });
+        if (stop_ && !task_)
+          return;
+        f = std::move(task_);
+        task_ = nullptr;
+      }
+      f();
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        busy_ = false;
+      }
+      cv_.notify_all();
+    }
+  }
+};
+std::vector<std::unique_ptr<Worker>> g_workers;
+
+void commit_host(unsigned curve_id, void* commitments, uint32_t num,
+                 const sxt_sequence_descriptor* d, const void* generators,
+                 uint64_t offset_generators, const char* fn) {
+  if (num == 0)
+    return;
+  std::lock_guard<std::mutex> lock(g_mutex);
+  require_init(fn);
+  B200_REQUIRE(commitments != nullptr, "commitments == nullptr");
+  (void)longest_column(d, num);  // validates the descriptors before any thread starts
+  if (curve_id != SXT_CURVE_RISTRETTO255)
+    B200_REQUIRE(generators != nullptr, "generators == nullptr");
+  const size_t stride = vt(curve_id).abi_commit_bytes;
+  const size_t parts = std::min<size_t>(g_workers.size() + 1, num);
+  if (parts <= 1) {
+    commit_on(g_state, curve_id, commitments, num, d, generators, offset_generators);
+    return;
+  }
+  // contiguous column chunks balanced by scalar bytes; chunk 0 runs on the calling thread
+  std::vector<uint64_t> prefix(num + 1, 0);
+  for (uint32_t i = 0; i < num; ++i)
+    prefix[i + 1] = prefix[i] + d[i].n * d[i].element_nbytes + 1;
+  std::vector<uint32_t> cut(parts + 1, num);
+  cut[0] = 0;
+  for (size_t p = 1; p < parts; ++p) {
+    uint32_t c = cut[p - 1] + 1;
+    while (c < num - (parts - p) && prefix[c] * parts < prefix[num] * p)
+      ++c;
+    cut[p] = c;
+  }
+  for (size_t p = 1; p < parts; ++p) {
+    Worker* w = g_workers[p - 1].get();
+    const uint32_t b = cut[p], e = cut[p + 1];
+    w->submit([=] {
+      commit_on(w->st, curve_id, static_cast<unsigned char*>(commitments) + b * stride, e - b,
+                d + b, generators, offset_generators);
+    });
+  }
+  commit_on(g_state, curve_id, commitments, cut[1], d, generators, offset_generators);
+  for (size_t p = 1; p < parts; ++p)
+    g_workers[p - 1]->wait();
 }
 
 Handle* handle_new(unsigned curve_id, const void* generators, unsigned n) {
@@ -384,6 +490,28 @@ int sxt_init(const struct sxt_config* config) {
     launch_builtin_generators(ctx(), g_state.builtin, 0, np);
     stream_sync(g_state.stream);
     g_state.num_builtin = np;
+  }
+  if (const char* env = std::getenv("BLITZAR_B200_DEVICES")) {
+    int want = std::atoi(env), count = 0;
+    B200_CUDA(cudaGetDeviceCount(&count));
+    want = std::min(want, count);
+    for (int k = 1; k < want; ++k) {
+      auto w = std::make_unique<Worker>((g_state.device + k) % count);
+      Worker* wp = w.get();
+      wp->submit([wp, np] {
+        init_device_state(wp->st);
+        if (np) {
+          B200_CUDA(cudaMalloc(&wp->st.builtin, np * kVTableEd25519.gen_bytes));
+          launch_builtin_generators(ctx_of(wp->st), wp->st.builtin, 0, np);
+          stream_sync(wp->st.stream);
+          wp->st.num_builtin = np;
+        }
+        wp->st.initialized = true;
+      });
+      wp->wait();
+      g_workers.push_back(std::move(w));
+    }
+    B200_CUDA(cudaSetDevice(g_state.device));
   }
   return 0;
 }

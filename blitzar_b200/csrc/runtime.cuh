@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <utility>
 #include <vector>
 
@@ -58,8 +59,8 @@ __global__ void __launch_bounds__(Body::kBlock, MinBlocks<Body>::value) k_run(Bo
 }
 
 struct LaunchCounter {
-  static unsigned long long& value() {
-    static unsigned long long v = 0;
+  static std::atomic<unsigned long long>& value() {
+    static std::atomic<unsigned long long> v{0};
     return v;
   }
 };
@@ -107,7 +108,7 @@ struct StagingRing {
   cudaEvent_t done[kSlots];
   size_t next = 0;
   static StagingRing& get() {
-    static StagingRing r;
+    static thread_local StagingRing r;  // one ring per host thread (= per device in multi-GPU mode)
     return r;
   }
   void* stage(stream_t s, const void* host, size_t bytes) {
@@ -141,7 +142,7 @@ struct KernelTimer {
   bool enabled = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans;
   static KernelTimer& get() {
-    static KernelTimer t;
+    static thread_local KernelTimer t;  // timings belong to the thread (device) that launched
     return t;
   }
   void begin(stream_t s) {

@@ -212,3 +212,40 @@ def test_upload_pieces_and_column_groups(bb, port, monkeypatch):
         assert np.array_equal(bb.compute_pedersen_commitments(0, cols, gens), want), (ranges, group_entries)
         assert np.array_equal(bb.compute_pedersen_commitments(0, cols[:2], None, 7),
                               port.commit(0, cols[:2], None, 7))
+
+
+_MULTI_DEVICE_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+import blitzar_b200.api as bb
+from oracle import port
+from tests import common
+port.build()
+assert bb.sxt_init(num_precomputed_generators=64) == 0
+rng = np.random.default_rng(77)
+for curve, n, shapes in ((0, 5000, [(0, 32, 0), (-100, 16, 1), (0, 1, 0), (-4999, 8, 0), (0, 4, 1)]),
+                         (1, 700, [(0, 32, 0), (0, 2, 0), (-3, 8, 1)]),
+                         (2, 900, [(0, 32, 0)] * 7), (3, 300, [(0, 16, 0), (0, 16, 1)])):
+    gens, _ = common.generators_for(port, curve, n)
+    cols = common.random_columns(rng, n, shapes)
+    got = bb.compute_pedersen_commitments(curve, cols, gens)
+    assert common.same(curve, got, port.commit(curve, cols, gens)), curve
+cols = common.random_columns(rng, 3000, [(0, 8, 0)] * 9)  # built-in generators on every device
+assert np.array_equal(bb.compute_pedersen_commitments(0, cols, None, 11), port.commit(0, cols, None, 11))
+print("multi-device ok")
+"""
+
+
+def test_columns_split_over_devices(bb):
+    """BLITZAR_B200_DEVICES=k: independent columns run on k devices of this process (the reference
+    splits by output the same way, sxt/multiexp/pippenger2/multiexponentiation.h:248-287)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, BLITZAR_B200_DEVICES=str(min(4, torch.cuda.device_count())))
+    r = subprocess.run([sys.executable, "-c", _MULTI_DEVICE_SCRIPT, root], env=env, cwd=root,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "multi-device ok" in r.stdout, r.stdout + r.stderr
