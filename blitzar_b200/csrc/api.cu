@@ -235,15 +235,23 @@ struct RangeWaitState {
   uint64_t n;
   uint32_t num_ranges;
   const State* st;
+  uint32_t uploaded;                     // pieces [0, uploaded) are already on the copy stream
+  std::function<void(uint32_t)> upload;  // enqueue (and, for pageable sources, stage) piece r
 };
 void wait_for_range(void* user, uint64_t begin, uint64_t end) {
   auto* w = static_cast<RangeWaitState*>(user);
-  // wait for every upload piece that intersects [begin, end) (column groups ask for all of them)
+  // wait for every upload piece that intersects [begin, end) (column groups ask for all of them).
+  // Pieces are put on the copy stream only now, one piece ahead of the compute being enqueued: a
+  // pageable source is staged by THIS thread (HostStager), and staging everything before the first
+  // kernel launch would serialise upload and compute.
   for (uint32_t r = 0; r < w->num_ranges; ++r) {
     const uint64_t rb = range_begin(w->n, r, w->num_ranges);
     const uint64_t re = range_begin(w->n, r + 1, w->num_ranges);
-    if (rb < end && begin < re)
+    if (rb < end && begin < re) {
+      while (w->uploaded <= std::min(r + 1, w->num_ranges - 1))
+        w->upload(w->uploaded++);
       B200_CUDA(cudaStreamWaitEvent(w->st->stream, w->st->range_events[r], 0));
+    }
   }
 }
 
@@ -268,18 +276,34 @@ void commit_on(const State& st, unsigned curve_id, void* commitments, uint32_t n
     dd[i].data = scal.p + off;
     off += ((size_t)d[i].n * d[i].element_nbytes + 31) & ~(size_t)31;
   }
-  // Two pieces for large single-/few-column calls (measured on B200, n = 2^20: 1 piece 7.26 ms,
-  // 2 pieces 6.86 ms, 4 pieces 7.49 ms — every extra piece costs ~0.4 ms of sort / cascade fixed
-  // work); many columns make the kernels dominate, so one piece.
-  uint32_t num_ranges = 1;
-  if (n >= (1ull << 19) && num <= 4)
-    num_ranges = 2;
+  // Upload in pieces so that sorting / accumulating piece r overlaps the PCIe copy of piece r+1
+  // (later pieces accumulate into a scratch bucket array and are merged, MergeBucketsBody). Measured
+  // on B200 through this call, pinned inputs, ristretto (tests/e2e_ranges.py), ms for 1/2/4/8 pieces:
+  //   1 column : n=2^18 2.60/2.51/3.10/3.96  2^20 6.80/5.87/5.51/6.88  2^22 23.7/20.1/17.8/16.8
+  //   4 columns: n=2^19 8.31/7.61/8.21/9.82  2^20 15.2/13.3/13.4/15.2  2^22 54.6/45.0/42.1/42.6
+  // every piece costs ~0.3 ms of fixed sort / cascade work, hence pieces of >= 2^18 terms.
+  uint32_t num_ranges = (uint32_t)std::min<uint64_t>(n >> 18, num == 1 ? 8 : 4);
+  if (num == 1 && n >= (1ull << 18))
+    num_ranges = std::max(num_ranges, 2u);
+  num_ranges = std::max(num_ranges, 1u);
   if (const char* env = std::getenv("BLITZAR_B200_RANGES"))
     num_ranges = (uint32_t)std::max(1, std::min(16, std::atoi(env)));
   // the destination buffers are stream-ordered allocations of the compute stream
   B200_CUDA(cudaEventRecord(st.alloc_event, s));
   B200_CUDA(cudaStreamWaitEvent(sc, st.alloc_event, 0));
-  for (uint32_t r = 0; r < num_ranges; ++r) {
+  // BLITZAR_B200_TRACE=1: device timeline of one call (upload pieces vs compute) on stderr
+  static const bool trace = std::getenv("BLITZAR_B200_TRACE") != nullptr;
+  std::vector<cudaEvent_t> tev;
+  auto mark = [&](cudaStream_t on) {
+    if (!trace)
+      return;
+    cudaEvent_t e;
+    B200_CUDA(cudaEventCreate(&e));
+    B200_CUDA(cudaEventRecord(e, on));
+    tev.push_back(e);
+  };
+  mark(sc);
+  auto upload = [&](uint32_t r) {
     const uint64_t b = range_begin(n, r, num_ranges), e = range_begin(n, r + 1, num_ranges);
     for (uint32_t i = 0; i < num; ++i) {
       const uint64_t lo = std::min<uint64_t>(b, d[i].n), hi = std::min<uint64_t>(e, d[i].n);
@@ -292,12 +316,26 @@ void commit_on(const State& st, unsigned curve_id, void* commitments, uint32_t n
                              static_cast<const unsigned char*>(generators) + b * V.abi_gen_bytes,
                              (e - b) * V.abi_gen_bytes, sc);
     B200_CUDA(cudaEventRecord(st.range_events[r], sc));
-  }
-  RangeWaitState w{n, num_ranges, &st};
+    mark(sc);
+  };
+  RangeWaitState w{n, num_ranges, &st, 0, upload};
   V.commit_device(ctx_of(st), out.p, nullptr, num, dd.data(), generators ? raw_gens.p : nullptr,
                   offset_generators, num_ranges, &wait_for_range, &w);
+  mark(s);
   copy_d2h(commitments, out.p, (size_t)num * V.abi_commit_bytes, s);
   stream_sync(s);
+  if (trace) {
+    std::fprintf(stderr, "blitzar_b200 trace: n=%llu cols=%u pieces=%u:", (unsigned long long)n, num,
+                 num_ranges);
+    for (size_t i = 1; i < tev.size(); ++i) {
+      float ms = 0;
+      B200_CUDA(cudaEventElapsedTime(&ms, tev[0], tev[i]));
+      std::fprintf(stderr, " %s%.3f", i + 1 == tev.size() ? "compute_done=" : "upload=", ms);
+    }
+    std::fprintf(stderr, " ms\n");
+    for (auto e : tev)
+      cudaEventDestroy(e);
+  }
 }
 
 // ---- optional in-process multi-GPU (BLITZAR_B200_DEVICES=k): independent columns are split over k

@@ -262,6 +262,25 @@ template <class C> struct FillIdentityBody {
   B200_HD void operator()(u64 t) const { p[t] = C::identity(); }
 };
 
+// buckets[k] += scratch[k] for every bucket the current generator range touched (bucket_end = the
+// range's cursor array after the scatter). A later range accumulates into its own scratch array and
+// is merged here: one coalesced pass, instead of a read-add-write at every run boundary of the
+// accumulation kernel (measured on B200, C2 in 4 pieces: 1.05 ms per piece that way vs 0.47 ms).
+template <class C> struct MergeBucketsBody {
+  static constexpr int kBlock = 128;
+  const u32* bucket_end;
+  const typename C::Point* scratch;
+  typename C::Point* buckets;
+  B200_HD void operator()(u64 k) const {
+    const u32 lo = k ? bucket_end[k - 1] : 0u;
+    if (bucket_end[k] == lo)
+      return;
+    typename C::Point b = buckets[k];
+    C::add(b, b, scratch[k]);
+    buckets[k] = b;
+  }
+};
+
 // Accumulator of the gathering level: the curve's Point, or its FP64-pipe form where the curve
 // provides one (ed25519).
 template <class C, class X, bool kFp64> struct GatherAcc {
@@ -295,22 +314,16 @@ template <class C, bool kGather, class X = SeqExec> struct AccumulateBody {
   const u32* m_ptr;                // number of entries at this level (device)
   u32 K;
   u32 final_level;
-  u32 add_into;                    // buckets already hold earlier generator chunks: add, don't store
   Point* buckets;
   u32* out_keys;
   Point* out_pieces;
   u32* out_m_ptr;
 
-  // every lane of a quad takes part in the addition; only the writer lane stores
+  // every bucket is written exactly once per generator range (a run strictly inside a chunk is
+  // complete; split runs travel down the cascade and are written by the level that completes them)
   B200_HD void put_bucket_guarded(u32 key, const Point& acc, bool writer) const {
-    if (add_into) {
-      Point b = buckets[key];
-      C::template add<X>(b, b, acc);
-      if (writer)
-        buckets[key] = b;
-    } else if (writer) {
+    if (writer)
       buckets[key] = acc;
-    }
   }
   B200_HD u32 key_at(u64 i) const { return kGather ? (u32)(entries[i] >> 32) : keys[i]; }
   B200_HD void fetch(Point& acc, u64 i, bool first) const {
@@ -634,7 +647,7 @@ inline MsmPlan msm_make_plan(std::vector<ColumnDesc> cols, const MsmOptions& opt
 
 // Sort + accumulate the terms [begin, end) of every column into d_buckets (indexed by the plan's
 // keys). gens[i] pairs with term i (absolute index). add_into: buckets already hold the sums of
-// earlier ranges. Enqueued on s.
+// earlier ranges (this range then goes through a scratch bucket array + MergeBucketsBody). Enqueued on s.
 template <class C>
 void msm_accumulate_range(stream_t s, const MsmPlan& plan, const typename C::Gen* gens, u64 begin,
                           u64 end, bool add_into, typename C::Point* d_buckets,
@@ -686,7 +699,9 @@ void msm_accumulate_range(stream_t s, const MsmPlan& plan, const typename C::Gen
   const u32 chunk1_auto = max_entries >= (1ull << 23) ? 64u : 32u;
   const u32 chunk1 = opt.chunk1 == 0 ? chunk1_auto : (opt.chunk1 < 4 ? 4u : opt.chunk1);
   const u32 chunkn = opt.chunkn < 4 ? 4u : opt.chunkn;
-  const u32 into = add_into ? 1u : 0u;
+  Point* d_target = d_buckets;
+  if (add_into)  // later ranges: own bucket array, merged into the shared one below
+    d_target = (Point*)dev_alloc(nkeys * sizeof(Point), s);
   u64 m_max = max_entries;
   u32 K = chunk1;
   const u32* lvl_keys = nullptr;
@@ -710,17 +725,17 @@ void msm_accumulate_range(stream_t s, const MsmPlan& plan, const typename C::Gen
     const u32 fin = final_level ? 1u : 0u;
     if (first) {
       KernelTimer::get().begin(s);
-      launch(AccumulateBody<C, true>{nullptr, d_entries, gens, nullptr, m_ptr, K, fin, into,
-                                     d_buckets, out_keys, out_pieces, out_m},
+      launch(AccumulateBody<C, true>{nullptr, d_entries, gens, nullptr, m_ptr, K, fin, d_target,
+                                     out_keys, out_pieces, out_m},
              T, s);
       KernelTimer::get().end(s);
     } else if (T <= opt.quad_threshold) {
       launch(AccumulateBody<C, false, QuadExec>{lvl_keys, nullptr, nullptr, lvl_pieces, m_ptr, K,
-                                                fin, into, d_buckets, out_keys, out_pieces, out_m},
+                                                fin, d_target, out_keys, out_pieces, out_m},
              T * QuadExec::kLanes, s);
     } else {
-      launch(AccumulateBody<C, false>{lvl_keys, nullptr, nullptr, lvl_pieces, m_ptr, K, fin, into,
-                                      d_buckets, out_keys, out_pieces, out_m},
+      launch(AccumulateBody<C, false>{lvl_keys, nullptr, nullptr, lvl_pieces, m_ptr, K, fin,
+                                      d_target, out_keys, out_pieces, out_m},
              T, s);
     }
     if (final_level)
@@ -732,6 +747,10 @@ void msm_accumulate_range(stream_t s, const MsmPlan& plan, const typename C::Gen
     m_max = 2 * T;
     K = chunkn;
     ++level;
+  }
+  if (add_into) {
+    launch(MergeBucketsBody<C>{d_counts, d_target, d_buckets}, nkeys, s);
+    dev_free(d_target, s);
   }
   for (void* ptr : to_free)
     dev_free(ptr, s);
