@@ -24,6 +24,25 @@ template <int OP> __global__ void k(u64* out, int iters) {
     if (OP == 3) {  // 64-bit integer add (IADD3 + IADD3.X)
       a0 += a1; a1 += a2; a2 += a3; a3 += a4; a4 += a5; a5 += a6; a6 += a7; a7 += a0;
     }
+    if (OP == 5) {  // IMAD.HI.U32
+      u32 x0 = (u32)a0, x1 = (u32)a1, x2 = (u32)a2, x3 = (u32)a3, x4 = (u32)a4, x5 = (u32)a5, x6 = (u32)a6, x7 = (u32)a7;
+      x0 = __umulhi(x0, m) + x1; x1 = __umulhi(x1, m) + x2; x2 = __umulhi(x2, m) + x3; x3 = __umulhi(x3, m) + x4;
+      x4 = __umulhi(x4, m) + x5; x5 = __umulhi(x5, m) + x6; x6 = __umulhi(x6, m) + x7; x7 = __umulhi(x7, m) + x0;
+      a0 = x0; a1 = x1; a2 = x2; a3 = x3; a4 = x4; a5 = x5; a6 = x6; a7 = x7;
+    }
+    if (OP == 6) {  // one 32x32 product accumulated into a 64-bit value WITHOUT IMAD.WIDE:
+                    // mul.lo + mul.hi on the multiplier pipe, add.cc + addc on the ALU pipe
+      u32 l[8] = {(u32)a0, (u32)a1, (u32)a2, (u32)a3, (u32)a4, (u32)a5, (u32)a6, (u32)a7};
+      u32 h[8] = {(u32)(a0 >> 32), (u32)(a1 >> 32), (u32)(a2 >> 32), (u32)(a3 >> 32), (u32)(a4 >> 32), (u32)(a5 >> 32), (u32)(a6 >> 32), (u32)(a7 >> 32)};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        u32 x = l[(j + 1) & 7], pl, ph;
+        asm volatile("mul.lo.u32 %0, %2, %3;\n\tmul.hi.u32 %1, %2, %3;" : "=r"(pl), "=r"(ph) : "r"(x), "r"(m));
+        asm volatile("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, %3;" : "+r"(l[j]), "+r"(h[j]) : "r"(pl), "r"(ph));
+      }
+      a0 = l[0] | ((u64)h[0] << 32); a1 = l[1] | ((u64)h[1] << 32); a2 = l[2] | ((u64)h[2] << 32); a3 = l[3] | ((u64)h[3] << 32);
+      a4 = l[4] | ((u64)h[4] << 32); a5 = l[5] | ((u64)h[5] << 32); a6 = l[6] | ((u64)h[6] << 32); a7 = l[7] | ((u64)h[7] << 32);
+    }
     if (OP == 4) {  // mixed: 8 DFMA + 8 IMAD.WIDE per iteration (do they overlap?)
       d0 = __fma_rz(d0, dm, d1); a0 += (u64)(u32)a1 * m; d1 = __fma_rz(d1, dm, d2); a1 += (u64)(u32)a2 * m;
       d2 = __fma_rz(d2, dm, d3); a2 += (u64)(u32)a3 * m; d3 = __fma_rz(d3, dm, d4); a3 += (u64)(u32)a4 * m;
@@ -51,5 +70,7 @@ int main() {
   run<2>("IMAD (32-bit)", d, 8);
   run<3>("64-bit integer add", d, 8);
   run<4>("8 DFMA + 8 IMAD.WIDE interleaved", d, 16);
+  run<5>("IMAD.HI.U32", d, 8);
+  run<6>("product via mul.lo+mul.hi+add.cc+addc", d, 8);
   printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
 }
