@@ -332,12 +332,31 @@ def run_cuda(args, rank, local_rank, world):
                          "kernel_ms": acc_avg_ms, "kernel_share_of_step": acc_avg_ms / (ms / args.steps),
                          "algorithmic_bytes_per_launch": BYTES_PER_TERM * n,
                          "note": "integer-ALU bound (about 16 point additions of 8-9 field "
-                                 "multiplications per term); see DESIGN.md"},
+                                 "multiplications per term); see DESIGN.md",
+                         "secondary": imad_roofline(n, acc_avg_ms, clocks)},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def imad_roofline(n, kernel_ms, clocks):
+    """The bound that actually limits the accumulation kernel: the 32x32->64 multiplier. One term
+    has 16 signed 16-bit digits (252-bit scalars), i.e. 16 bucket entries; every entry except the
+    first of a bucket run is one cached-form addition = 8 field multiplications = 8 x (64 + 8)
+    IMAD.WIDE.U32 (schoolbook 8x8 limbs + the 2^256 = 38 fold). Peak = 29.2 lane-ops/clk/SM measured
+    on B200 for the multiply-accumulate-with-carry form this kernel issues (tests/micro/pipes.cu;
+    plain IMAD.WIDE 23.0, IMAD.HI 24.6) x 148 SMs x the SM clock sampled during the run."""
+    windows, nbuckets = 16, 1 << 15
+    entries = windows * n * (1.0 - 2.0 ** -16)  # zero digits are skipped
+    runs = windows * nbuckets * (1.0 - (1.0 - 1.0 / nbuckets) ** (entries / windows))
+    imads = (entries - runs) * 8 * 72
+    mhz = clocks.get("sm_mhz") or 1965.0
+    peak = 29.2 * 148 * mhz * 1e6
+    achieved = imads / (kernel_ms * 1e-3)
+    return {"bound": "imad_wide", "achieved": achieved, "peak": peak, "unit": "IMAD.WIDE lane-ops/s",
+            "frac": achieved / peak, "imad_wide_per_launch": imads}
 
 
 def main():
