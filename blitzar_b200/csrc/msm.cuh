@@ -197,15 +197,18 @@ struct ScatterBody {
   }
 };
 
-// exclusive prefix sum, three index-parallel passes per level
-constexpr u32 kScanChunk = 256;
+// exclusive prefix sum, three index-parallel passes per level. The first level uses short chunks
+// (many threads, each walking 256 contiguous bytes); the partial sums above it are few, so they take
+// long chunks to keep the recursion at two levels for the usual 2^19 keys.
+constexpr u32 kScanChunk = 256, kScanChunkFirst = 64;
 struct ScanUpBody {
   static constexpr int kBlock = 128;
   const u32* in;
   u64 n;
   u32* partial;
+  u32 chunk;
   B200_HD void operator()(u64 t) const {
-    u64 b = t * kScanChunk, e = b + kScanChunk < n ? b + kScanChunk : n;
+    u64 b = t * chunk, e = b + chunk < n ? b + chunk : n;
     u32 s = 0;
     for (u64 i = b; i < e; ++i)
       s += in[i];
@@ -230,8 +233,9 @@ struct ScanDownBody {
   u32* data;  // in: counts, out: exclusive offsets
   u64 n;
   const u32* partial_scanned;
+  u32 chunk;
   B200_HD void operator()(u64 t) const {
-    u64 b = t * kScanChunk, e = b + kScanChunk < n ? b + kScanChunk : n;
+    u64 b = t * chunk, e = b + chunk < n ? b + chunk : n;
     u32 s = partial_scanned[t];
     for (u64 i = b; i < e; ++i) {
       u32 v = data[i];
@@ -243,16 +247,16 @@ struct ScanDownBody {
 
 // in-place exclusive scan of data[0..n); data[n] is included in the scan so that data[n] = total
 // when the caller zeroes it beforehand.
-inline void exclusive_scan(u32* data, u64 n, stream_t s) {
+inline void exclusive_scan(u32* data, u64 n, stream_t s, u32 chunk = kScanChunkFirst) {
   if (n <= kScanChunk) {
     launch(ScanTopBody{data, n}, 1, s);
     return;
   }
-  u64 m = (n + kScanChunk - 1) / kScanChunk;
+  u64 m = (n + chunk - 1) / chunk;
   u32* partial = (u32*)dev_alloc(m * sizeof(u32), s);
-  launch(ScanUpBody{data, n, partial}, m, s);
-  exclusive_scan(partial, m, s);
-  launch(ScanDownBody{data, n, partial}, m, s);
+  launch(ScanUpBody{data, n, partial, chunk}, m, s);
+  exclusive_scan(partial, m, s, kScanChunk);
+  launch(ScanDownBody{data, n, partial, chunk}, m, s);
   dev_free(partial, s);
 }
 
