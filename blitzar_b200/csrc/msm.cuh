@@ -325,7 +325,7 @@ template <class C, bool kGather, class X = SeqExec> struct AccumulateBody {
 
   // every bucket is written exactly once per generator range (a run strictly inside a chunk is
   // complete; split runs travel down the cascade and are written by the level that completes them)
-  B200_HD void put_bucket_guarded(u32 key, const Point& acc, bool writer) const {
+  B200_HD void put_bucket(u32 key, const Point& acc, bool writer) const {
     if (writer)
       buckets[key] = acc;
   }
@@ -382,7 +382,7 @@ template <class C, bool kGather, class X = SeqExec> struct AccumulateBody {
         } else {
           ga.get(acc);
           if (final_level || !first_seg) {
-            put_bucket_guarded(cur, acc, writer);
+            put_bucket(cur, acc, writer);
           } else if (writer) {
             out_keys[2 * t] = cur;
             out_pieces[2 * t] = acc;
@@ -404,7 +404,7 @@ template <class C, bool kGather, class X = SeqExec> struct AccumulateBody {
           fetch(acc, i, false);
         } else {
           if (final_level || !first_seg) {
-            put_bucket_guarded(cur, acc, writer);
+            put_bucket(cur, acc, writer);
           } else if (writer) {
             out_keys[2 * t] = cur;
             out_pieces[2 * t] = acc;
@@ -416,7 +416,7 @@ template <class C, bool kGather, class X = SeqExec> struct AccumulateBody {
       }
     }
     if (final_level) {
-      put_bucket_guarded(cur, acc, writer);
+      put_bucket(cur, acc, writer);
       return;
     }
     if (!writer)

@@ -214,6 +214,35 @@ def test_upload_pieces_and_column_groups(bb, port, monkeypatch):
                               port.commit(0, cols[:2], None, 7))
 
 
+@pytest.mark.parametrize("curve", [1, 2, 3])
+def test_upload_pieces_weierstrass(bb, port, curve, monkeypatch):
+    """Later upload pieces go through the scratch bucket array + MergeBucketsBody on every curve."""
+    rng = np.random.default_rng(40 + curve)
+    n = 3000
+    gens, _ = common.generators_for(port, curve, n)
+    cols = common.random_columns(rng, n, [(0, 32, 0), (-1000, 16, 1), (-2999, 32, 0)])
+    want = port.commit(curve, cols, gens)
+    for ranges in ("2", "4"):
+        monkeypatch.setenv("BLITZAR_B200_RANGES", ranges)
+        assert common.same(curve, bb.compute_pedersen_commitments(curve, cols, gens), want), ranges
+
+
+def test_default_piece_count_large_n(bb):
+    """n = 2^19 + 7 takes the default multi-piece upload (no env override): compare with the
+    single-piece path on the same inputs, and with the homomorphic split of the range."""
+    rng = np.random.default_rng(51)
+    n = (1 << 19) + 7
+    s = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    cols = [(s, 0), (s[: n - 12345, :8].copy(), 1)]
+    got = bb.compute_pedersen_commitments(0, cols)
+    os.environ["BLITZAR_B200_RANGES"] = "1"
+    try:
+        one = bb.compute_pedersen_commitments(0, cols)
+    finally:
+        del os.environ["BLITZAR_B200_RANGES"]
+    assert np.array_equal(got, one)
+
+
 _MULTI_DEVICE_SCRIPT = r"""
 import sys, numpy as np
 sys.path.insert(0, sys.argv[1])
