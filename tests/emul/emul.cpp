@@ -112,12 +112,21 @@ extern "C" int emul_check_mul(unsigned field_id, unsigned iters, unsigned seed) 
       for (int i = 0; i < 8; ++i) { a.l[i] = next(); b.l[i] = next(); }
       if (it % 7 == 0) for (int i = 0; i < 8; ++i) a.l[i] = 0xffffffffu;
       if (it % 11 == 0) for (int i = 0; i < 8; ++i) b.l[i] = 0xffffffffu;
+      // Karatsuba corner cases: equal / zero halves, halves in either order
+      if (it % 13 == 0) for (int i = 0; i < 4; ++i) a.l[4 + i] = a.l[i];
+      if (it % 17 == 0) for (int i = 0; i < 4; ++i) b.l[i] = b.l[4 + i];
+      if (it % 19 == 0) for (int i = 0; i < 4; ++i) a.l[i] = 0;
+      if (it % 23 == 0) for (int i = 0; i < 4; ++i) b.l[4 + i] = 0;
+      if (it % 29 == 0) for (int i = 0; i < 8; ++i) a.l[i] = 0;
       F25519::mul(r1, a, b);
       F25519::mul_ref(r2, a, b);
       F25519::canonical(c1, r1);
       F25519::canonical(c2, r2);
       for (int i = 0; i < 8; ++i) if (c1.l[i] != c2.l[i]) { ++bad; break; }
       F25519::mul_lat(r1, a, b);
+      F25519::canonical(c1, r1);
+      for (int i = 0; i < 8; ++i) if (c1.l[i] != c2.l[i]) { ++bad; break; }
+      F25519::mul_kara(r1, a, b);
       F25519::canonical(c1, r1);
       for (int i = 0; i < 8; ++i) if (c1.l[i] != c2.l[i]) { ++bad; break; }
     }

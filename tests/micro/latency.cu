@@ -36,6 +36,7 @@ template <int OP> __global__ void k_thr(Fe<8>* io, int iters) {
     if (OP == 0) F::mul(a, a, b);
     if (OP == 1) F::mul_lat(a, a, b);
     if (OP == 2) F::mul_ref(a, a, b);
+    if (OP == 3) F::mul_kara(a, a, b);
   }
   if (a.l[0] == 0x12345678u) io[8] = a;
 }
@@ -126,6 +127,7 @@ int main() {
   thr<0>("F25519::mul (chains)", d);
   thr<1>("F25519::mul_lat (columns)", d);
   thr<2>("F25519::mul_ref (plain C)", d);
+  thr<3>("F25519::mul_kara (Karatsuba)", d);
   thr_k("F25519D::mul (fp64 pipe)", k_thr_fp64, d, 256, 8);
   thr_k("F25519D::mul (fp64 pipe)", k_thr_fp64, d, 128, 3);
   thr_k("accd_add_gen (fp64 point add)", k_thr_accd, d, 128, 3);
