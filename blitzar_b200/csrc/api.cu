@@ -30,6 +30,7 @@ struct State {
   int device = -1;
   cudaStream_t stream = nullptr;       // every kernel of the engine
   cudaStream_t copy_stream = nullptr;  // host-to-device staging of the C-ABI calls
+  cudaStream_t tail_stream = nullptr;  // cascade + bucket merge of upload piece k, under piece k+1
   cudaEvent_t range_events[16] = {};
   cudaEvent_t alloc_event = nullptr;
   void* builtin = nullptr;  // g(0..num_builtin) device-resident, ed25519 generator layout
@@ -39,6 +40,12 @@ struct State {
 State g_state;  // the primary device: every entry point runs here
 EngineCtx ctx_of(const State& st) {
   EngineCtx c{st.stream, g_state.opt, st.builtin, st.num_builtin};
+  static const bool tail_on = [] {
+    const char* env = std::getenv("BLITZAR_B200_TAIL_STREAM");
+    return env != nullptr && std::atoi(env) != 0;  // off by default (measured: no gain)
+  }();
+  if (tail_on)
+    c.tail = st.tail_stream;
   if (const char* env = std::getenv("BLITZAR_B200_GROUP_ENTRIES"))  // test hook: force column groups
     c.opt.max_group_entries = std::strtoull(env, nullptr, 10);
   return c;
@@ -50,6 +57,9 @@ void init_device_state(State& st) {
   B200_CUDA(cudaSetDevice(st.device));
   B200_CUDA(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
   B200_CUDA(cudaStreamCreateWithFlags(&st.copy_stream, cudaStreamNonBlocking));
+  int prio_low = 0, prio_high = 0;  // the tail's small kernels must not queue behind a bulk kernel's blocks
+  B200_CUDA(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
+  B200_CUDA(cudaStreamCreateWithPriority(&st.tail_stream, cudaStreamNonBlocking, prio_high));
   for (auto& e : st.range_events)
     B200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   B200_CUDA(cudaEventCreateWithFlags(&st.alloc_event, cudaEventDisableTiming));

@@ -56,7 +56,7 @@ template <class C> struct CurveOps {
       if (!whole && hook && b == 0)
         hook->before_range(0, ~0ull);
       msm_run<C>(ctx.s, gens, group, out + b, ctx.opt, whole ? num_ranges : 1,
-                 whole ? hook : nullptr);
+                 whole ? hook : nullptr, ctx.tail);
       b = e;
     }
   }

@@ -25,6 +25,7 @@ struct EngineCtx {
   MsmOptions opt;
   const void* builtin;  // device-resident built-in ristretto generators g(0..num_builtin)
   uint64_t num_builtin;
+  stream_t tail = stream_t();  // optional second stream: cascade + merge of piece k under piece k+1
 };
 
 struct Handle {

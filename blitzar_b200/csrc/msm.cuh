@@ -651,11 +651,14 @@ inline MsmPlan msm_make_plan(std::vector<ColumnDesc> cols, const MsmOptions& opt
 
 // Sort + accumulate the terms [begin, end) of every column into d_buckets (indexed by the plan's
 // keys). gens[i] pairs with term i (absolute index). add_into: buckets already hold the sums of
-// earlier ranges (this range then goes through a scratch bucket array + MergeBucketsBody). Enqueued on s.
+// earlier ranges (this range then goes through a scratch bucket array + MergeBucketsBody). Enqueued on
+// s; with tail != s the latency-bound part (cascade levels >= 2, merge) moves to `tail` right after
+// the first level, so that it runs under the NEXT range's sort and first level (the caller joins
+// `tail` back before the bucket reduction).
 template <class C>
 void msm_accumulate_range(stream_t s, const MsmPlan& plan, const typename C::Gen* gens, u64 begin,
                           u64 end, bool add_into, typename C::Point* d_buckets,
-                          u32* d_window_used, const MsmOptions& opt) {
+                          u32* d_window_used, const MsmOptions& opt, stream_t tail) {
   typedef typename C::Point Point;
   const u32 ncols = plan.ncols;
   std::vector<ColumnDesc> cols(plan.cols);
@@ -714,6 +717,7 @@ void msm_accumulate_range(stream_t s, const MsmPlan& plan, const typename C::Gen
   std::vector<void*> to_free;
   bool first = true;
   int level = 0;
+  stream_t cs = s;  // stream of the current cascade level
   for (;;) {
     bool final_level = m_max <= K;
     u64 T = (m_max + K - 1) / K;
@@ -721,8 +725,8 @@ void msm_accumulate_range(stream_t s, const MsmPlan& plan, const typename C::Gen
     Point* out_pieces = nullptr;
     u32* out_m = d_m + 1 + (level % 8);
     if (!final_level) {
-      out_keys = (u32*)dev_alloc(2 * T * sizeof(u32), s);
-      out_pieces = (Point*)dev_alloc(2 * T * sizeof(Point), s);
+      out_keys = (u32*)dev_alloc(2 * T * sizeof(u32), cs);
+      out_pieces = (Point*)dev_alloc(2 * T * sizeof(Point), cs);
       to_free.push_back(out_keys);
       to_free.push_back(out_pieces);
     }
@@ -733,14 +737,18 @@ void msm_accumulate_range(stream_t s, const MsmPlan& plan, const typename C::Gen
                                      out_keys, out_pieces, out_m},
              T, s);
       KernelTimer::get().end(s);
+      if (tail != s) {
+        stream_follow(tail, s);
+        cs = tail;
+      }
     } else if (T <= opt.quad_threshold) {
       launch(AccumulateBody<C, false, QuadExec>{lvl_keys, nullptr, nullptr, lvl_pieces, m_ptr, K,
                                                 fin, d_target, out_keys, out_pieces, out_m},
-             T * QuadExec::kLanes, s);
+             T * QuadExec::kLanes, cs);
     } else {
       launch(AccumulateBody<C, false>{lvl_keys, nullptr, nullptr, lvl_pieces, m_ptr, K, fin,
                                       d_target, out_keys, out_pieces, out_m},
-             T, s);
+             T, cs);
     }
     if (final_level)
       break;
@@ -753,14 +761,14 @@ void msm_accumulate_range(stream_t s, const MsmPlan& plan, const typename C::Gen
     ++level;
   }
   if (add_into) {
-    launch(MergeBucketsBody<C>{d_counts, d_target, d_buckets}, nkeys, s);
-    dev_free(d_target, s);
+    launch(MergeBucketsBody<C>{d_counts, d_target, d_buckets}, nkeys, cs);
+    dev_free(d_target, cs);
   }
   for (void* ptr : to_free)
-    dev_free(ptr, s);
+    dev_free(ptr, cs);
   dev_free(d_entries, s);
-  dev_free(d_m, s);
-  dev_free(d_counts, s);
+  dev_free(d_m, cs);
+  dev_free(d_counts, cs);
   dev_free(d_stage, s);
 }
 
@@ -836,7 +844,7 @@ struct RangeHook {
 template <class C>
 void msm_run(stream_t s, const typename C::Gen* gens, std::vector<ColumnDesc> cols,
              typename C::Point* out, const MsmOptions& opt = MsmOptions(), u32 num_ranges = 1,
-             RangeHook* hook = nullptr) {
+             RangeHook* hook = nullptr, stream_t tail = stream_t()) {
   typedef typename C::Point Point;
   if (cols.empty())
     return;
@@ -858,12 +866,17 @@ void msm_run(stream_t s, const typename C::Gen* gens, std::vector<ColumnDesc> co
   const u64 needed = (plan.total_entries + limit - 1) / limit;
   if (needed > num_ranges)
     num_ranges = (u32)std::min<u64>(needed, plan.max_n);
+  // several ranges + a second stream: the cascade / merge of range r runs under range r+1
+  const bool overlap = num_ranges > 1 && tail != stream_t() && tail != s;
   for (u32 r = 0; r < num_ranges; ++r) {
     u64 begin = range_begin(plan.max_n, r, num_ranges), end = range_begin(plan.max_n, r + 1, num_ranges);
     if (hook)
       hook->before_range(begin, end);
-    msm_accumulate_range<C>(s, plan, gens, begin, end, r > 0, d_buckets, d_window_used, opt);
+    msm_accumulate_range<C>(s, plan, gens, begin, end, r > 0, d_buckets, d_window_used, opt,
+                            overlap ? tail : s);
   }
+  if (overlap)
+    stream_follow(s, tail);
   msm_finish<C>(s, plan, d_buckets, d_window_used, out, opt);
   dev_free(d_window_used, s);
   dev_free(d_buckets, s);

@@ -97,6 +97,16 @@ inline void copy_d2d(void* d, const void* s_, size_t bytes, stream_t s) {
     B200_CUDA(cudaMemcpyAsync(d, s_, bytes, cudaMemcpyDeviceToDevice, s));
 }
 inline void stream_sync(stream_t s) { B200_CUDA(cudaStreamSynchronize(s)); }
+// everything enqueued on `later` from here on waits for what is on `earlier` now
+inline void stream_follow(stream_t later, stream_t earlier) {
+  static thread_local cudaEvent_t ring[64];
+  static thread_local unsigned next = 0;
+  cudaEvent_t& e = ring[next++ % 64];
+  if (!e)
+    B200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  B200_CUDA(cudaEventRecord(e, earlier));
+  B200_CUDA(cudaStreamWaitEvent(later, e, 0));
+}
 
 // Small host->device parameter blocks (column descriptors, prefix tables). A pageable
 // cudaMemcpyAsync synchronises the stream, which would stall the launch queue once per range; the
@@ -207,6 +217,7 @@ inline void copy_h2d(void* d, const void* h, size_t bytes, stream_t) { std::memc
 inline void copy_d2h(void* h, const void* d, size_t bytes, stream_t) { std::memcpy(h, d, bytes); }
 inline void copy_d2d(void* d, const void* s_, size_t bytes, stream_t) { std::memcpy(d, s_, bytes); }
 inline void stream_sync(stream_t) {}
+inline void stream_follow(stream_t, stream_t) {}
 inline void* stage_to_device(stream_t s, const void* host, size_t bytes) {
   void* d = dev_alloc(bytes, s);
   std::memcpy(d, host, bytes);
