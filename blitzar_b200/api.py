@@ -36,6 +36,7 @@ B200_SYMBOLS = [
     "b200_combine_partials_device", "b200_fixed_msm_device",
     "b200_combine_partials_projective_device", "b200_set_tuning", "b200_profile_accumulate",
     "b200_profile_read", "b200_set_reduce_groups", "b200_stream",
+    "b200_synthetic_generators_device",
 ]
 
 
@@ -255,6 +256,22 @@ def commit_device(curve_id, columns_shape, scalar_ptrs, generators_ptr, out_comm
     lib().b200_commit_device(C.c_uint(curve_id), C.c_void_p(out_commit_ptr),
                              C.c_void_p(out_partial_ptr), C.c_uint32(num), arr,
                              C.c_void_p(generators_ptr), C.c_uint64(offset_generators))
+
+
+def synthetic_generators_device(curve_id, out_ptr, n, first=0, projective=False):
+    """b200_synthetic_generators_device: the reference benchmarks' generators, produced in HBM."""
+    lib().b200_synthetic_generators_device(C.c_uint(curve_id), C.c_void_p(out_ptr), C.c_uint64(n),
+                                           C.c_uint64(first), C.c_int(1 if projective else 0))
+
+
+def synthetic_generators(curve_id, n, first=0, projective=False):
+    """Host copy of synthetic_generators_device (uint8 [n, stride])."""
+    stride = CURVE_SIZES[curve_id][0 if (projective or curve_id == 0) else 1]
+    buf = DeviceBuffer(n * stride)
+    synthetic_generators_device(curve_id, buf.ptr, n, first, projective)
+    out = buf.to_host((n, stride))
+    buf.free()
+    return out
 
 
 def synchronize():

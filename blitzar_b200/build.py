@@ -52,11 +52,29 @@ def build_product(verbose=False):
 
 
 def build_emul():
-    src = os.path.join(ROOT, "tests", "emul", "emul.cpp")
-    out = os.path.join(ROOT, "tests", "emul", "libb200_emul.so")
-    if _newer(out, [src] + _headers()):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-DB200_EMULATE", "-fPIC", "-shared", "-w",
-                               src, "-o", out])
+    """CPU emulation harness (test infrastructure): the per-curve units of the product compiled as
+    host C++ (-DB200_EMULATE, tests/emul/emul_prefix.h force-included), in parallel."""
+    edir = os.path.join(ROOT, "tests", "emul")
+    out = os.path.join(edir, "libb200_emul.so")
+    objdir = os.path.join(edir, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    prefix = os.path.join(edir, "emul_prefix.h")
+    flags = ["g++", "-std=c++17", "-O1", "-DB200_EMULATE", "-fPIC", "-w", "-include", prefix]
+    jobs, objs = [], []
+    for u in [x for x in UNITS if x.startswith("curve_")] + ["emul.cpp"]:
+        src = os.path.join(edir if u == "emul.cpp" else CSRC, u)
+        obj = os.path.join(objdir, u.rsplit(".", 1)[0] + ".o")
+        objs.append(obj)
+        if _newer(obj, [src, prefix] + _headers()):
+            jobs.append((u, subprocess.Popen(flags + ["-x", "c++", "-c", src, "-o", obj],
+                                             stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+    for u, p in jobs:
+        o, _ = p.communicate()
+        if p.returncode:
+            sys.stderr.write(o.decode())
+            raise RuntimeError(f"emulation build failed for {u}")
+    if jobs or not os.path.exists(out):
+        subprocess.check_call(["g++", "-shared", "-o", out] + objs)
     return out
 
 

@@ -895,6 +895,15 @@ void b200_fixed_msm_device(void* out_res, void* out_partials,
   vt(h->curve_id).fixed_device(ctx(), out_res, out_partials, h, mode, element_num_bytes,
                                output_bit_table, output_lengths, num_outputs, rows, scalars);
 }
+void b200_synthetic_generators_device(unsigned curve_id, void* out_generators, uint64_t n,
+                                      uint64_t first, int projective) {
+  if (n == 0)
+    return;
+  std::lock_guard<std::mutex> lock(g_mutex);
+  require_init("b200_synthetic_generators_device");
+  B200_REQUIRE(out_generators != nullptr, "out_generators == nullptr");
+  vt(curve_id).synth_generators(ctx(), out_generators, n, first, projective != 0);
+}
 void b200_set_reduce_groups(unsigned g1, unsigned gn) {
   std::lock_guard<std::mutex> lock(g_mutex);
   auto pow2 = [](unsigned v, unsigned dflt) {

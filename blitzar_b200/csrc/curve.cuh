@@ -534,6 +534,17 @@ template <class FieldT, class CP> struct Weierstrass {
     return p;
   }
   static B200_HD bool gen_is_identity(const Gen& g) { return F::is_zero(g.y) && F::is_zero(g.x); }
+  // the subgroup generator the reference derives its random test / benchmark points from
+  // (curve_g1/constant/generator.h:34-66, curve_bng1/..., curve_gk/...)
+  static B200_HD Gen subgroup_generator() {
+    Gen g;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      g.x.l[i] = F::Params::gx(i);
+      g.y.l[i] = F::Params::gy(i);
+    }
+    return g;
+  }
   static B200_HD void neg(Point& r, const Point& a) {
     r.X = a.X;
     F::neg(r.Y, a.Y);

@@ -7,6 +7,7 @@
 
 #include "engine_api.cuh"
 #include "msm.cuh"
+#include "synth.cuh"
 
 namespace b200 {
 
@@ -199,6 +200,10 @@ template <class C> struct CurveOps {
                         void* out_pts) {
     launch(SumPartsBody<C>{(const Point*)parts, nparts, count, (Point*)out_pts}, count, ctx.s);
   }
+  static void synth_generators(const EngineCtx& ctx, void* out_dev, uint64_t n, uint64_t first,
+                               bool projective) {
+    Synth<C>::generators(ctx.s, out_dev, n, first, projective);
+  }
 };
 
 #define B200_DEFINE_CURVE_VTABLE(NAME, C)                                                          \
@@ -213,6 +218,7 @@ template <class C> struct CurveOps {
                             &CurveOps<C>::ingest_projective,                                       \
                             &CurveOps<C>::gens_to_projective,                                      \
                             &CurveOps<C>::store,                                                   \
-                            &CurveOps<C>::sum_parts}
+                            &CurveOps<C>::sum_parts,                                               \
+                            &CurveOps<C>::synth_generators}
 
 }  // namespace b200

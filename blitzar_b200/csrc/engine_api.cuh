@@ -67,6 +67,9 @@ struct CurveVTable {
   void (*store)(const EngineCtx&, const void* pts, void* out_dev, uint64_t count, bool commit);
   void (*sum_parts)(const EngineCtx&, const void* parts, uint32_t nparts, uint32_t count,
                     void* out_pts);
+  // synthetic generators (synth.cuh) in the ABI layout: projective structs or commit-stride affine
+  void (*synth_generators)(const EngineCtx&, void* out_dev, uint64_t n, uint64_t first,
+                           bool projective);
 };
 extern const CurveVTable kVTableEd25519, kVTableBls12381, kVTableBn254, kVTableGrumpkin;
 

@@ -591,6 +591,7 @@ struct F25519 {
 // Mont<P>: Montgomery residues, fully reduced. P supplies N, p(i), one(i), r2(i), inv.
 // ------------------------------------------------------------------------------------------------
 template <class P> struct Mont {
+  typedef P Params;
   static constexpr int N = P::N;
   typedef Fe<N> E;
 
@@ -827,6 +828,8 @@ struct BnParams {
   static B200_HD u32 r2(int i) { return BN_R2(i); }
   static B200_HD u32 pm2(int i) { return BN_PM2(i); }
   static B200_HD u32 half(int i) { return BN_HALF(i); }
+  static B200_HD u32 gx(int i) { return BN_GX(i); }
+  static B200_HD u32 gy(int i) { return BN_GY(i); }
 };
 struct GkParams {
   static constexpr int N = 8;
@@ -836,6 +839,8 @@ struct GkParams {
   static B200_HD u32 r2(int i) { return GK_R2(i); }
   static B200_HD u32 pm2(int i) { return GK_PM2(i); }
   static B200_HD u32 half(int i) { return GK_HALF(i); }
+  static B200_HD u32 gx(int i) { return GK_GX(i); }
+  static B200_HD u32 gy(int i) { return GK_GY(i); }
 };
 struct BlsParams {
   static constexpr int N = 12;
@@ -845,6 +850,8 @@ struct BlsParams {
   static B200_HD u32 r2(int i) { return BLS_R2(i); }
   static B200_HD u32 pm2(int i) { return BLS_PM2(i); }
   static B200_HD u32 half(int i) { return BLS_HALF(i); }
+  static B200_HD u32 gx(int i) { return BLS_GX(i); }
+  static B200_HD u32 gy(int i) { return BLS_GY(i); }
 };
 typedef Mont<BnParams> FBn;
 typedef Mont<GkParams> FGk;

@@ -151,6 +151,19 @@ B200_HD void for_each_digit(const u32 v[8], bool negative, const ColumnDesc& col
 }
 
 // ---- kernels (index-parallel bodies) -------------------------------------------------------------
+// column of global term index tid: the last j with col_start[j] <= tid (binary search, so that
+// many-output calls — hundreds of narrow columns — do not pay O(columns) loads per term)
+B200_HD u32 column_of(const u64* col_start, u32 ncols, u64 tid) {
+  u32 lo = 0, hi = ncols;
+  while (hi - lo > 1) {
+    const u32 mid = (lo + hi) >> 1;
+    if (tid >= col_start[mid])
+      lo = mid;
+    else
+      hi = mid;
+  }
+  return lo;
+}
 struct CountBody {
   static constexpr int kBlock = 256;
   const ColumnDesc* cols;
@@ -158,9 +171,7 @@ struct CountBody {
   u32 ncols, c, nbuckets;
   u32* counts;
   B200_HD void operator()(u64 tid) const {
-    u32 j = 0;
-    while (j + 1 < ncols && tid >= col_start[j + 1])
-      ++j;
+    const u32 j = column_of(col_start, ncols, tid);
     const ColumnDesc col = cols[j];
     u64 i = tid - col_start[j];
     u32 v[8];
@@ -179,9 +190,7 @@ struct ScatterBody {
   u32* cursor;  // exclusive offsets, consumed
   u64* entries;  // (key << 32) | (generator index << 1) | negate
   B200_HD void operator()(u64 tid) const {
-    u32 j = 0;
-    while (j + 1 < ncols && tid >= col_start[j + 1])
-      ++j;
+    const u32 j = column_of(col_start, ncols, tid);
     const ColumnDesc col = cols[j];
     u64 i = tid - col_start[j];
     u32 v[8];

@@ -113,7 +113,7 @@ inline void stream_follow(stream_t later, stream_t earlier) {
 // blocks therefore go through a ring of pinned slots and are copied truly asynchronously. A slot is
 // reused only after the copy that last read it has completed (per-slot event).
 struct StagingRing {
-  static constexpr size_t kSlotBytes = 16384, kSlots = 256;
+  static constexpr size_t kSlotBytes = 65536, kSlots = 128;  // 64 KiB = ~1600 column descriptors
   unsigned char* base = nullptr;
   cudaEvent_t done[kSlots];
   size_t next = 0;

@@ -198,6 +198,13 @@ void b200_fixed_msm_device(void* out_res, void* out_partials,
 void b200_combine_partials_projective_device(unsigned curve_id, void* out_res,
                                              const void* partials, uint32_t num_parts,
                                              uint32_t count);
+/* Synthetic benchmark / test inputs generated in HBM (device pointer out): the generators the
+ * reference's own benchmarks use — ristretto255: built-in g(first + i) as sxt_ristretto255 structs;
+ * other curves: generate_random_element with fast_random_number_generator{i + 1, i + 2}
+ * (cbindings/pedersen.t.cc:81-123, benchmark/multi_exp_pip/benchmark.m.cc:84-95), as projective
+ * *_p2 structs (projective != 0, handle input) or affine structs at the commitment stride. */
+void b200_synthetic_generators_device(unsigned curve_id, void* out_generators, uint64_t n,
+                                      uint64_t first, int projective);
 /* Per-launch CUDA-event timing of the dominant kernel (level-1 bucket accumulation) on the library
  * stream: enable, run, then read the total milliseconds and launch count since the last read. */
 void b200_profile_accumulate(int enable);

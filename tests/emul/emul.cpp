@@ -5,23 +5,21 @@
 // MSM pipeline — digit recoding, counting sort, chunked accumulation cascade, bucket reduction,
 // window combination, canonicalisation — can be checked against the oracle in a container without
 // a GPU. The product library (api.cu) has no such path and aborts without a GPU.
-#define __host__
-#define __device__
-#define __global__
-#define __forceinline__ inline __attribute__((always_inline))
-#include <cstdint>
-struct uint4 { uint32_t x, y, z, w; };
-#include "../../blitzar_b200/csrc/engine.cuh"
-#include "../../blitzar_b200/csrc/ipa.cuh"
+//
+// The per-curve translation units of the product (csrc/curve_*.cu) are compiled as host C++ with
+// emul_prefix.h force-included and reached through the same type-erased vtables api.cu uses.
+#include "emul_prefix.h"
+#include "../../blitzar_b200/csrc/engine_api.cuh"
+#include "../../blitzar_b200/csrc/fp64field.cuh"
 
 using namespace b200;
 
-template <class F> static auto dispatch(unsigned curve_id, F f) {
+static const CurveVTable& vt(unsigned curve_id) {
   switch (curve_id) {
-  case kRistretto255: return f(Ed25519{});
-  case kBls12381: return f(Bls12381G1{});
-  case kBn254: return f(Bn254G1{});
-  default: return f(GrumpkinG{});
+  case 0: return kVTableEd25519;
+  case 1: return kVTableBls12381;
+  case 2: return kVTableBn254;
+  default: return kVTableGrumpkin;
   }
 }
 
@@ -42,36 +40,36 @@ void emul_commit(unsigned curve_id, void* out_commitments, uint32_t num,
                  const sxt_sequence_descriptor* d, const void* generators, uint64_t offset) {
   if (num == 0) return;
   EngineCtx ctx{0, g_opt, nullptr, 0};
-  dispatch(curve_id, [&](auto c) {
-    CurveOps<decltype(c)>::commit_device(ctx, out_commitments, nullptr, num, d, generators, offset,
-                                         g_ranges, nullptr, nullptr);
-    return 0;
-  });
+  vt(curve_id).commit_device(ctx, out_commitments, nullptr, num, d, generators, offset, g_ranges,
+                             nullptr, nullptr);
 }
 void emul_get_generators(void* out160, uint64_t num, uint64_t offset) {
-  std::vector<Ed25519::Gen> g(num);
-  launch(BuiltinGeneratorBody{g.data(), offset}, num, 0);
-  launch(GenToProjBody<Ed25519>{g.data(), (unsigned char*)out160}, num, 0);
+  EngineCtx ctx{0, g_opt, nullptr, 0};
+  std::vector<unsigned char> g((num ? num : 1) * vt(0).gen_bytes);
+  launch_builtin_generators(ctx, g.data(), offset, num);
+  vt(0).gens_to_projective(ctx, g.data(), out160, num);
+}
+// same contract as b200_synthetic_generators_device (host memory)
+void emul_synth_generators(unsigned curve_id, void* out, uint64_t n, uint64_t first, int projective) {
+  EngineCtx ctx{0, g_opt, nullptr, 0};
+  vt(curve_id).synth_generators(ctx, out, n, first, projective != 0);
 }
 // handle_new + fixed MSM in one call (mode as in b200_fixed_msm_device)
 void emul_fixed(unsigned curve_id, void* res, const void* generators_proj, unsigned num_gens,
                 int mode, unsigned element_num_bytes, const unsigned* bit_table,
                 const unsigned* lengths, unsigned num_outputs, unsigned n, const uint8_t* scalars) {
   EngineCtx ctx{0, g_opt, nullptr, 0};
-  dispatch(curve_id, [&](auto c) {
-    typedef decltype(c) C;
-    std::vector<typename C::Gen> gens(num_gens ? num_gens : 1);
-    launch(IngestBody<C, true>{(const unsigned char*)generators_proj, gens.data()}, num_gens, 0);
-    Handle h{curve_id, num_gens, gens.data()};
-    unsigned rows = n;
-    if (mode == 2) {
-      rows = 0;
-      for (unsigned j = 0; j < num_outputs; ++j) rows = lengths[j] > rows ? lengths[j] : rows;
-    }
-    CurveOps<C>::fixed_device(ctx, res, nullptr, &h, mode, element_num_bytes, bit_table, lengths,
-                    num_outputs, rows, scalars);
-    return 0;
-  });
+  const CurveVTable& V = vt(curve_id);
+  std::vector<unsigned char> gens((size_t)(num_gens ? num_gens : 1) * V.gen_bytes);
+  V.ingest_projective(ctx, generators_proj, gens.data(), num_gens);
+  Handle h{curve_id, num_gens, gens.data()};
+  unsigned rows = n;
+  if (mode == 2) {
+    rows = 0;
+    for (unsigned j = 0; j < num_outputs; ++j) rows = lengths[j] > rows ? lengths[j] : rows;
+  }
+  V.fixed_device(ctx, res, nullptr, &h, mode, element_num_bytes, bit_table, lengths, num_outputs,
+                 rows, scalars);
 }
 }
 
@@ -140,29 +138,23 @@ extern "C" int emul_check_mul(unsigned field_id, unsigned iters, unsigned seed) 
 
 // multi-GPU host logic support: partial accumulator points and their combination
 extern "C" unsigned emul_point_bytes(unsigned curve_id) {
-  return dispatch(curve_id, [](auto c) { return (unsigned)sizeof(typename decltype(c)::Point); });
+  return vt(curve_id).point_bytes;
 }
 extern "C" void emul_commit_partial(unsigned curve_id, void* out_partials, uint32_t num,
                                     const sxt_sequence_descriptor* d, const void* generators,
                                     uint64_t offset) {
   if (num == 0) return;
   EngineCtx ctx{0, g_opt, nullptr, 0};
-  dispatch(curve_id, [&](auto c) {
-    CurveOps<decltype(c)>::commit_device(ctx, nullptr, out_partials, num, d, generators, offset,
-                                         g_ranges, nullptr, nullptr);
-    return 0;
-  });
+  vt(curve_id).commit_device(ctx, nullptr, out_partials, num, d, generators, offset, g_ranges,
+                             nullptr, nullptr);
 }
 extern "C" void emul_combine_partials(unsigned curve_id, void* out_commitments, const void* partials,
                                       uint32_t num_parts, uint32_t count) {
   EngineCtx ctx{0, g_opt, nullptr, 0};
-  dispatch(curve_id, [&](auto c) {
-    typedef decltype(c) C;
-    std::vector<typename C::Point> sum(count);
-    CurveOps<C>::sum_parts(ctx, partials, num_parts, count, sum.data());
-    CurveOps<C>::store(ctx, sum.data(), out_commitments, count, true);
-    return 0;
-  });
+  const CurveVTable& V = vt(curve_id);
+  std::vector<unsigned char> sum((size_t)count * V.point_bytes);
+  V.sum_parts(ctx, partials, num_parts, count, sum.data());
+  V.store(ctx, sum.data(), out_commitments, count, true);
 }
 
 // FP64-pipe field multiplication (exact integer semantics) vs the plain reference schedule
@@ -213,13 +205,13 @@ extern "C" void emul_prove_inner_product(uint8_t* l_vector, uint8_t* r_vector, u
                                          uint8_t* transcript203, uint64_t n, uint64_t offset,
                                          const uint8_t* a_vector, const uint8_t* b_vector) {
   EngineCtx ctx{0, g_opt, nullptr, 0};
-  Ipa::prove(ctx, l_vector, r_vector, ap_value, transcript203, n, offset, a_vector, b_vector);
+  ipa_prove(ctx, l_vector, r_vector, ap_value, transcript203, n, offset, a_vector, b_vector);
 }
 extern "C" int emul_verify_inner_product(uint8_t* transcript203, uint64_t n, uint64_t offset,
                                          const uint8_t* b_vector, const uint8_t* product,
                                          const uint8_t* a_commit160, const uint8_t* l_vector,
                                          const uint8_t* r_vector, const uint8_t* ap_value) {
   EngineCtx ctx{0, g_opt, nullptr, 0};
-  return Ipa::verify(ctx, transcript203, n, offset, b_vector, product, a_commit160, l_vector,
-                     r_vector, ap_value);
+  return ipa_verify(ctx, transcript203, n, offset, b_vector, product, a_commit160, l_vector,
+                    r_vector, ap_value);
 }

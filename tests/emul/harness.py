@@ -25,13 +25,11 @@ _lib = None
 
 
 def build():
-    csrc = os.path.join(ROOT, "blitzar_b200", "csrc")
-    deps = [SRC] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
-    if not os.path.exists(LIB_PATH) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH)
-                                           for d in deps):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-DB200_EMULATE", "-fPIC", "-shared",
-                               "-w", SRC, "-o", LIB_PATH])
-    return LIB_PATH
+    import sys
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    from blitzar_b200 import build as b
+    return b.build_emul()
 
 
 def lib():
@@ -157,3 +155,11 @@ def verify_inner_product(transcript, b, product, a_commit, l_vector, r_vector, a
         C.c_void_p(b.ctypes.data), C.c_void_p(np.ascontiguousarray(product).ctypes.data),
         C.c_void_p(np.ascontiguousarray(a_commit).ctypes.data), C.c_void_p(lv.ctypes.data),
         C.c_void_p(rv.ctypes.data), C.c_void_p(np.ascontiguousarray(ap_value).ctypes.data)))
+
+
+def synth_generators(curve_id, n, first=0, projective=False):
+    stride = SIZES[curve_id][0 if (projective or curve_id == 0) else 1]
+    out = np.zeros((n, stride), dtype=np.uint8)
+    lib().emul_synth_generators(C.c_uint(curve_id), C.c_void_p(out.ctypes.data), C.c_uint64(n),
+                                C.c_uint64(first), C.c_int(1 if projective else 0))
+    return out
