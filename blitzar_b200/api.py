@@ -36,7 +36,8 @@ B200_SYMBOLS = [
     "b200_combine_partials_device", "b200_fixed_msm_device",
     "b200_combine_partials_projective_device", "b200_set_tuning", "b200_profile_accumulate",
     "b200_profile_read", "b200_set_reduce_groups", "b200_stream",
-    "b200_synthetic_generators_device",
+    "b200_synthetic_generators_device", "b200_commit_host_partials",
+    "b200_fixed_msm_host_partials", "b200_multiexp_handle_new_device",
 ]
 
 
@@ -68,6 +69,7 @@ def lib():
         L.b200_launch_count.restype = C.c_ulonglong
         L.b200_point_bytes.restype = C.c_uint
         L.b200_malloc.restype = C.c_void_p
+        L.b200_multiexp_handle_new_device.restype = C.c_void_p
         L.b200_event_create.restype = C.c_void_p
         L.b200_stream.restype = C.c_void_p
         L.b200_event_elapsed_ms.restype = C.c_float
@@ -159,9 +161,12 @@ def get_one_commit(n):
 class MultiexpHandle:
     """sxt_multiexp_handle: device-resident generators for fixed-base MSM."""
 
-    def __init__(self, curve_id, generators=None, filename=None):
+    def __init__(self, curve_id, generators=None, filename=None, device_ptr=None, n=None):
         self.curve_id = curve_id
-        if filename is not None:
+        if device_ptr is not None:  # projective ABI structs already in HBM
+            self.h = lib().b200_multiexp_handle_new_device(C.c_uint(curve_id),
+                                                           C.c_void_p(device_ptr), C.c_uint(n))
+        elif filename is not None:
             self.h = lib().sxt_multiexp_handle_new_from_file(C.c_uint(curve_id),
                                                              filename.encode())
         else:
@@ -272,6 +277,35 @@ def synthetic_generators(curve_id, n, first=0, projective=False):
     out = buf.to_host((n, stride))
     buf.free()
     return out
+
+
+def commit_host_partials(curve_id, columns, generators, out_partial_ptr, offset_generators=0):
+    """b200_commit_host_partials: host columns / generators in, partial points in HBM out."""
+    desc, keep = make_descriptors(columns)
+    lib().b200_commit_host_partials(C.c_uint(curve_id), C.c_void_p(out_partial_ptr),
+                                    C.c_uint32(len(columns)), desc, _ptr(generators),
+                                    C.c_uint64(offset_generators))
+
+
+def fixed_msm_device(handle, out_res_ptr, out_partial_ptr, element_num_bytes, num_outputs, n,
+                     scalars_ptr):
+    """b200_fixed_msm_device, fixed-width mode."""
+    lib().b200_fixed_msm_device(C.c_void_p(out_res_ptr), C.c_void_p(out_partial_ptr),
+                                C.c_void_p(handle.h), C.c_int(0), C.c_uint(element_num_bytes),
+                                None, None, C.c_uint(num_outputs), C.c_uint(n),
+                                C.c_void_p(scalars_ptr))
+
+
+def fixed_msm_host_partials(handle, out_partial_ptr, element_num_bytes, num_outputs, n, scalars):
+    lib().b200_fixed_msm_host_partials(C.c_void_p(out_partial_ptr), C.c_void_p(handle.h),
+                                       C.c_int(0), C.c_uint(element_num_bytes), None, None,
+                                       C.c_uint(num_outputs), C.c_uint(n), _ptr(scalars))
+
+
+def combine_partials_projective_device(curve_id, out_ptr, partials_ptr, num_parts, count):
+    lib().b200_combine_partials_projective_device(C.c_uint(curve_id), C.c_void_p(out_ptr),
+                                                  C.c_void_p(partials_ptr), C.c_uint32(num_parts),
+                                                  C.c_uint32(count))
 
 
 def synchronize():

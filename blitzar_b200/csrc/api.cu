@@ -266,9 +266,11 @@ void wait_for_range(void* user, uint64_t begin, uint64_t end) {
 }
 
 // the commitments of `num` columns on one device (the calling thread's current device is st.device)
+// Results: `commitments` (host, canonical) or, when out_partials_dev is given instead, the internal
+// accumulator points in device memory (multi-GPU callers combine them).
 void commit_on(const State& st, unsigned curve_id, void* commitments, uint32_t num,
                const sxt_sequence_descriptor* d, const void* generators,
-               uint64_t offset_generators) {
+               uint64_t offset_generators, void* out_partials_dev = nullptr) {
   const CurveVTable& V = vt(curve_id);
   cudaStream_t s = st.stream, sc = st.copy_stream;
   uint64_t n = longest_column(d, num);
@@ -329,10 +331,12 @@ void commit_on(const State& st, unsigned curve_id, void* commitments, uint32_t n
     mark(sc);
   };
   RangeWaitState w{n, num_ranges, &st, 0, upload};
-  V.commit_device(ctx_of(st), out.p, nullptr, num, dd.data(), generators ? raw_gens.p : nullptr,
-                  offset_generators, num_ranges, &wait_for_range, &w);
+  V.commit_device(ctx_of(st), out_partials_dev ? nullptr : out.p, out_partials_dev, num, dd.data(),
+                  generators ? raw_gens.p : nullptr, offset_generators, num_ranges, &wait_for_range,
+                  &w);
   mark(s);
-  copy_d2h(commitments, out.p, (size_t)num * V.abi_commit_bytes, s);
+  if (!out_partials_dev)
+    copy_d2h(commitments, out.p, (size_t)num * V.abi_commit_bytes, s);
   stream_sync(s);
   if (trace) {
     std::fprintf(stderr, "blitzar_b200 trace: n=%llu cols=%u pieces=%u:", (unsigned long long)n, num,
@@ -453,16 +457,22 @@ void commit_host(unsigned curve_id, void* commitments, uint32_t num,
     g_workers[p - 1]->wait();
 }
 
-Handle* handle_new(unsigned curve_id, const void* generators, unsigned n) {
+// generators: n projective ABI structs, in host memory or (device_resident) already in HBM
+Handle* handle_new(unsigned curve_id, const void* generators, unsigned n,
+                   bool device_resident = false) {
   const CurveVTable& V = vt(curve_id);
   cudaStream_t s = g_state.stream;
   Handle* h = new Handle{curve_id, n, nullptr};
   B200_CUDA(cudaMalloc(&h->gens, (size_t)(n ? n : 1) * V.gen_bytes));
   if (n) {
     B200_REQUIRE(generators != nullptr, "generators == nullptr");
-    DevBuf<unsigned char> raw((size_t)n * V.abi_proj_bytes, s);
-    HostStager::get().copy(raw.p, generators, (size_t)n * V.abi_proj_bytes, s);
-    V.ingest_projective(ctx(), raw.p, h->gens, n);
+    if (device_resident) {
+      V.ingest_projective(ctx(), generators, h->gens, n);
+    } else {
+      DevBuf<unsigned char> raw((size_t)n * V.abi_proj_bytes, s);
+      HostStager::get().copy(raw.p, generators, (size_t)n * V.abi_proj_bytes, s);
+      V.ingest_projective(ctx(), raw.p, h->gens, n);
+    }
     stream_sync(s);
   }
   return h;
@@ -470,7 +480,7 @@ Handle* handle_new(unsigned curve_id, const void* generators, unsigned n) {
 
 void fixed_host(void* res, const Handle* h, int mode, unsigned element_num_bytes,
                 const unsigned* bit_table, const unsigned* lengths, unsigned num_outputs,
-                unsigned n, const uint8_t* scalars) {
+                unsigned n, const uint8_t* scalars, void* out_partials_dev = nullptr) {
   if (num_outputs == 0)
     return;
   cudaStream_t s = g_state.stream;
@@ -490,9 +500,10 @@ void fixed_host(void* res, const Handle* h, int mode, unsigned element_num_bytes
   const CurveVTable& V = vt(h->curve_id);
   DevBuf<unsigned char> out((size_t)num_outputs * V.abi_proj_bytes, s);
   HostStager::get().copy(scal.p, scalars, bytes, s);
-  V.fixed_device(ctx(), out.p, nullptr, h, mode, element_num_bytes, bit_table, lengths,
-                 num_outputs, rows, scal.p);
-  copy_d2h(res, out.p, (size_t)num_outputs * V.abi_proj_bytes, s);
+  V.fixed_device(ctx(), out_partials_dev ? nullptr : out.p, out_partials_dev, h, mode,
+                 element_num_bytes, bit_table, lengths, num_outputs, rows, scal.p);
+  if (!out_partials_dev)
+    copy_d2h(res, out.p, (size_t)num_outputs * V.abi_proj_bytes, s);
   stream_sync(s);
 }
 
@@ -855,6 +866,38 @@ void b200_commit_device(unsigned curve_id, void* out_commitments, void* out_part
   require_init("b200_commit_device");
   vt(curve_id).commit_device(ctx(), out_commitments, out_partials, num_sequences, descriptors,
                              generators, offset_generators, 1, nullptr, nullptr);
+}
+void b200_commit_host_partials(unsigned curve_id, void* out_partials,
+                               uint32_t num_sequences,
+                               const struct sxt_sequence_descriptor* descriptors,
+                               const void* generators, uint64_t offset_generators) {
+  if (num_sequences == 0)
+    return;
+  std::lock_guard<std::mutex> lock(g_mutex);
+  require_init("b200_commit_host_partials");
+  B200_REQUIRE(out_partials != nullptr, "out_partials == nullptr");
+  commit_on(g_state, curve_id, nullptr, num_sequences, descriptors, generators, offset_generators,
+            out_partials);
+}
+void b200_fixed_msm_host_partials(void* out_partials, const struct sxt_multiexp_handle* handle,
+                                  int mode, unsigned element_num_bytes,
+                                  const unsigned* output_bit_table, const unsigned* output_lengths,
+                                  unsigned num_outputs, unsigned n, const uint8_t* scalars) {
+  if (num_outputs == 0)
+    return;
+  std::lock_guard<std::mutex> lock(g_mutex);
+  require_init("b200_fixed_msm_host_partials");
+  const Handle* h = reinterpret_cast<const Handle*>(handle);
+  B200_REQUIRE(h != nullptr && out_partials != nullptr, "null handle or out_partials");
+  fixed_host(nullptr, h, mode, element_num_bytes, output_bit_table, output_lengths, num_outputs, n,
+             scalars, out_partials);
+}
+struct sxt_multiexp_handle* b200_multiexp_handle_new_device(unsigned curve_id,
+                                                            const void* generators_dev,
+                                                            unsigned n) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  require_init("b200_multiexp_handle_new_device");
+  return reinterpret_cast<sxt_multiexp_handle*>(handle_new(curve_id, generators_dev, n, true));
 }
 void b200_combine_partials_device(unsigned curve_id, void* out_commitments, const void* partials,
                                   uint32_t num_parts, uint32_t count) {

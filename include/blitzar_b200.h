@@ -184,6 +184,23 @@ void b200_event_destroy(void* event);
 void b200_commit_device(unsigned curve_id, void* out_commitments, void* out_partials,
                         uint32_t num_sequences, const struct sxt_sequence_descriptor* descriptors,
                         const void* generators, uint64_t offset_generators);
+/* The host-pointer commitment call (same copy / compute pipeline as the sxt_*_commitments entry
+ * points: descriptors[i].data and generators are HOST pointers) that leaves one internal accumulator
+ * point per column in DEVICE memory instead of canonical commitments — the per-rank half of a
+ * generator-range-sharded multi-GPU commitment. Synchronises before returning. */
+void b200_commit_host_partials(unsigned curve_id, void* out_partials, uint32_t num_sequences,
+                               const struct sxt_sequence_descriptor* descriptors,
+                               const void* generators, uint64_t offset_generators);
+/* as the three sxt_fixed_* calls (host scalars; mode 0 fixed width, 1 packed, 2 vlen), partial
+ * accumulator points to device memory */
+void b200_fixed_msm_host_partials(void* out_partials, const struct sxt_multiexp_handle* handle,
+                                  int mode, unsigned element_num_bytes,
+                                  const unsigned* output_bit_table, const unsigned* output_lengths,
+                                  unsigned num_outputs, unsigned n, const uint8_t* scalars);
+/* sxt_multiexp_handle_new over generators that already sit in HBM (projective ABI structs) */
+struct sxt_multiexp_handle* b200_multiexp_handle_new_device(unsigned curve_id,
+                                                            const void* generators_dev,
+                                                            unsigned n);
 /* out[j] = sum_r partials[r * count + j]; writes canonical commitments (device pointer). */
 void b200_combine_partials_device(unsigned curve_id, void* out_commitments, const void* partials,
                                   uint32_t num_parts, uint32_t count);

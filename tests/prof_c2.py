@@ -13,9 +13,7 @@ rng = np.random.default_rng(0)
 if curve == 0:
     gens = bb.get_generators(n, 0)
 else:
-    from oracle import refcpu
-    base = refcpu.random_elements(curve, 1024)[1]
-    gens = np.tile(base, (n // 1024 + 1, 1))[:n].copy()
+    gens = bb.synthetic_generators(curve, n, 0, projective=False)  # distinct points
 s = rng.integers(0, 256, (n, 32), dtype=np.uint8)
 s[:, 31] &= 0x0f
 dg = bb.DeviceBuffer(host=gens)

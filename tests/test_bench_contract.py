@@ -31,6 +31,6 @@ def test_multiplier_roofline_accounting():
     import bench
     r = bench.imad_roofline(1 << 20, 1.63, {"sm_mhz": 1965.0})
     # 16 windows x 2^20 entries, minus one run start per non-empty bucket, x 8 muls x 72 products
-    assert 9.0e9 < r["imad_wide_per_launch"] < 9.7e9
+    assert 9.0e9 < r["imad_wide_per_step"] < 9.7e9
     assert r["bound"] == "imad_wide" and 0.5 < r["frac"] < 1.0
     assert abs(r["peak"] - 29.2 * 148 * 1965e6) < 1e6
