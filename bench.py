@@ -297,7 +297,7 @@ def run_workload(env, name, scaling, steps, warmup, with_e2e=True, sampler=None)
     d_partial = torch.zeros((ncol, pb), dtype=torch.uint8, device="cuda")
     d_all = torch.zeros((world, ncol, pb), dtype=torch.uint8, device="cuda")
     res_stride = proj_stride if fixed else out_bytes
-    d_out = torch.zeros((ncol, max(res_stride, 64)), dtype=torch.uint8, device="cuda")
+    d_out = torch.zeros((ncol * res_stride + 64,), dtype=torch.uint8, device="cuda")
     shapes = [(n, 32, 0)] * ncol
     scal_ptrs = [d.data_ptr() for d in d_scal]
     exchange = world > 1 and not by_column
@@ -320,7 +320,7 @@ def run_workload(env, name, scaling, steps, warmup, with_e2e=True, sampler=None)
         if exchange:
             combine()
 
-    out_host = env.pinned((ncol, max(res_stride, 64)))
+    out_host = env.pinned((ncol * res_stride + 64,))
 
     def step_e2e(columns=None, gens=None):
         """host buffers in, host result out — the plugin call a consumer makes (per rank: the same
@@ -337,8 +337,8 @@ def run_workload(env, name, scaling, steps, warmup, with_e2e=True, sampler=None)
             bb.commit_host_partials(curve, cols, g, d_partial.data_ptr(), first if builtin else 0)
         combine()
         bb.lib().b200_memcpy_d2h(C.c_void_p(out_host.data_ptr()), C.c_void_p(d_out.data_ptr()),
-                                 C.c_uint64(ncol * d_out.shape[1]))
-        return out_host.numpy()[:, :res_stride].copy()
+                                 C.c_uint64(ncol * res_stride))
+        return out_host.numpy()[:ncol * res_stride].reshape(ncol, res_stride).copy()
 
     # ---- device-resident timing --------------------------------------------------------------------
     for _ in range(warmup):
@@ -358,7 +358,7 @@ def run_workload(env, name, scaling, steps, warmup, with_e2e=True, sampler=None)
     launches = bb.launch_count() - launches0
     acc_ms, acc_launches = bb.profile_read()
     bb.profile_accumulate(False)
-    dev_result = d_out.cpu().numpy()[:, :res_stride].copy()
+    dev_result = d_out.cpu().numpy()[:ncol * res_stride].reshape(ncol, res_stride).copy()
 
     # ---- end-to-end timing -------------------------------------------------------------------------
     t_e2e, e2e_result = None, None

@@ -33,13 +33,17 @@ struct State {
   cudaStream_t tail_stream = nullptr;  // cascade + bucket merge of upload piece k, under piece k+1
   cudaEvent_t range_events[16] = {};
   cudaEvent_t alloc_event = nullptr;
-  void* builtin = nullptr;  // g(0..num_builtin) device-resident, ed25519 generator layout
+  void* builtin = nullptr;  // g(0..num_builtin) device-resident, ed25519 generator layout,
+                            // followed by windows 1.. of their fixed-base table
   uint64_t num_builtin = 0;
+  unsigned builtin_window_bits = 0, builtin_windows = 0;
   MsmOptions opt;
 };
 State g_state;  // the primary device: every entry point runs here
 EngineCtx ctx_of(const State& st) {
   EngineCtx c{st.stream, g_state.opt, st.builtin, st.num_builtin};
+  c.builtin_window_bits = st.builtin_window_bits;
+  c.builtin_windows = st.builtin_windows;
   static const bool tail_on = [] {
     const char* env = std::getenv("BLITZAR_B200_TAIL_STREAM");
     return env != nullptr && std::atoi(env) != 0;  // off by default (measured: no gain)
@@ -48,6 +52,8 @@ EngineCtx ctx_of(const State& st) {
     c.tail = st.tail_stream;
   if (const char* env = std::getenv("BLITZAR_B200_GROUP_ENTRIES"))  // test hook: force column groups
     c.opt.max_group_entries = std::strtoull(env, nullptr, 10);
+  if (const char* env = std::getenv("BLITZAR_B200_TABLE_POLICY"))  // 1 = always use tables, 2 = never
+    c.opt.table_policy = (u32)std::atoi(env);
   return c;
 }
 EngineCtx ctx() { return ctx_of(g_state); }
@@ -84,6 +90,37 @@ void ensure_device() {
       B200_CUDA(cudaGetDevice(&g_state.device));
   }
   init_device_state(g_state);
+}
+
+// Window width of a fixed-base table over n generators of a curve on the current device: at most
+// 40 % of the free HBM (180 GB per B200: n = 2^24 bn254 generators take 14 GB at c = 20), overridable
+// with BLITZAR_B200_TABLE_WINDOW (0 disables tables).
+unsigned choose_table_window(uint64_t n, size_t gen_bytes) {
+  if (const char* env = std::getenv("BLITZAR_B200_TABLE_WINDOW")) {
+    const int c = std::atoi(env);
+    if (c <= 0)
+      return 0;
+    const unsigned cc = (unsigned)std::min(22, std::max(8, c));
+    return (uint64_t)(256 / cc + 1) * n < (1ull << 31) ? cc : 0;
+  }
+  size_t free_b = 0, total_b = 0;
+  B200_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  return table_window_bits(n, gen_bytes, 0.4 * (double)free_b);
+}
+
+// device array of `windows` x n generators; window 0 = g(0 .. n) built in, the rest their table
+void make_builtin_table(State& st, uint64_t np) {
+  const CurveVTable& V = kVTableEd25519;
+  const unsigned c = choose_table_window(np, V.gen_bytes);
+  const unsigned windows = c ? 256 / c + 1 : 1;
+  B200_CUDA(cudaMalloc(&st.builtin, (size_t)np * windows * V.gen_bytes));
+  EngineCtx cx = ctx_of(st);
+  launch_builtin_generators(cx, st.builtin, 0, np);
+  V.build_table(cx, st.builtin, np, c, windows);
+  stream_sync(st.stream);
+  st.num_builtin = np;
+  st.builtin_window_bits = c;
+  st.builtin_windows = windows;
 }
 
 void require_init(const char* fn) {
@@ -457,22 +494,33 @@ void commit_host(unsigned curve_id, void* commitments, uint32_t num,
     g_workers[p - 1]->wait();
 }
 
-// generators: n projective ABI structs, in host memory or (device_resident) already in HBM
+// generators: n projective ABI structs (host memory, or device_resident: already in HBM), or —
+// compact_window != 0 — the table image of a reference partition-table file (host memory).
+// Builds the fixed-base table 2^(c w) G_i on the device (replaces the reference's CPU-serial
+// make_in_memory_partition_table_accessor, in_memory_partition_table_accessor_utility.h:41-79).
 Handle* handle_new(unsigned curve_id, const void* generators, unsigned n,
-                   bool device_resident = false) {
+                   bool device_resident = false, unsigned compact_window = 0,
+                   size_t compact_bytes = 0) {
   const CurveVTable& V = vt(curve_id);
   cudaStream_t s = g_state.stream;
   Handle* h = new Handle{curve_id, n, nullptr};
-  B200_CUDA(cudaMalloc(&h->gens, (size_t)(n ? n : 1) * V.gen_bytes));
+  h->window_bits = choose_table_window(n, V.gen_bytes);
+  h->windows = h->window_bits ? 256 / h->window_bits + 1 : 1;
+  B200_CUDA(cudaMalloc(&h->gens, (size_t)(n ? n : 1) * h->windows * V.gen_bytes));
   if (n) {
     B200_REQUIRE(generators != nullptr, "generators == nullptr");
-    if (device_resident) {
+    if (compact_window) {
+      DevBuf<unsigned char> raw(compact_bytes, s);
+      HostStager::get().copy(raw.p, generators, compact_bytes, s);
+      V.ingest_compact_table(ctx(), raw.p, compact_window, h->gens, n);
+    } else if (device_resident) {
       V.ingest_projective(ctx(), generators, h->gens, n);
     } else {
       DevBuf<unsigned char> raw((size_t)n * V.abi_proj_bytes, s);
       HostStager::get().copy(raw.p, generators, (size_t)n * V.abi_proj_bytes, s);
       V.ingest_projective(ctx(), raw.p, h->gens, n);
     }
+    V.build_table(ctx(), h->gens, n, h->window_bits, h->windows);
     stream_sync(s);
   }
   return h;
@@ -544,12 +592,8 @@ int sxt_init(const struct sxt_config* config) {
   ensure_device();
   g_state.initialized = true;
   uint64_t np = config->num_precomputed_generators;
-  if (np) {
-    B200_CUDA(cudaMalloc(&g_state.builtin, np * kVTableEd25519.gen_bytes));
-    launch_builtin_generators(ctx(), g_state.builtin, 0, np);
-    stream_sync(g_state.stream);
-    g_state.num_builtin = np;
-  }
+  if (np)
+    make_builtin_table(g_state, np);
   if (const char* env = std::getenv("BLITZAR_B200_DEVICES")) {
     int want = std::atoi(env), count = 0;
     B200_CUDA(cudaGetDeviceCount(&count));
@@ -559,12 +603,8 @@ int sxt_init(const struct sxt_config* config) {
       Worker* wp = w.get();
       wp->submit([wp, np] {
         init_device_state(wp->st);
-        if (np) {
-          B200_CUDA(cudaMalloc(&wp->st.builtin, np * kVTableEd25519.gen_bytes));
-          launch_builtin_generators(ctx_of(wp->st), wp->st.builtin, 0, np);
-          stream_sync(wp->st.stream);
-          wp->st.num_builtin = np;
-        }
+        if (np)
+          make_builtin_table(wp->st, np);
         wp->st.initialized = true;
       });
       wp->wait();
@@ -721,9 +761,10 @@ void sxt_multiexp_handle_free(struct sxt_multiexp_handle* handle) {
   delete h;
 }
 
-// File format (ours, versioned; the reference's [u32 window_width][partition table] format,
-// in_memory_partition_table_accessor.h:42-59, describes a different precomputation):
-//   u32 magic "B2HD", u32 version = 1, u32 curve_id, u32 n, then n projective ABI structs.
+// File format written (versioned): u32 magic "B2HD", u32 version = 1, u32 curve_id, u32 n, then n
+// projective ABI structs — the generators; the fixed-base table is rebuilt on load (a fraction of a
+// second on the device, against the file being 13-26x larger with it). sxt_multiexp_handle_new_from_
+// file also reads the reference's [u32 window_width][partition table] files (see there).
 void sxt_multiexp_handle_write_to_file(const struct sxt_multiexp_handle* handle,
                                        const char* filename) {
   std::lock_guard<std::mutex> lock(g_mutex);
@@ -753,9 +794,31 @@ struct sxt_multiexp_handle* sxt_multiexp_handle_new_from_file(unsigned curve_id,
   B200_REQUIRE(filename != nullptr, "null filename");
   FILE* f = std::fopen(filename, "rb");
   B200_REQUIRE(f != nullptr, "cannot open handle file");
-  uint32_t hdr[4];
-  B200_REQUIRE(std::fread(hdr, sizeof(hdr), 1, f) == 1, "short handle file");
-  B200_REQUIRE(hdr[0] == kHandleMagic && hdr[1] == 1u, "not a blitzar_b200 handle file");
+  uint32_t hdr[4] = {0, 0, 0, 0};
+  B200_REQUIRE(std::fread(hdr, sizeof(uint32_t), 1, f) == 1, "short handle file");
+  if (hdr[0] != kHandleMagic) {
+    // The reference's own format (in_memory_partition_table_accessor.h:42-59,98-105):
+    // [u32 window_width][table of compact elements], 2^w subset sums per group of w generators.
+    // Entry (1 << j) of group g is generator g*w + j, so the generators are recovered exactly and
+    // this library's table is rebuilt from them on the device (groups padded with the identity stay
+    // identities, as in the reference).
+    const unsigned w = hdr[0];
+    const size_t esz = vt(curve_id).abi_compact_bytes;
+    B200_REQUIRE(w >= 1 && w <= 24, "not a handle file (bad window width)");
+    std::fseek(f, 0, SEEK_END);
+    const size_t bytes = (size_t)std::ftell(f) - sizeof(uint32_t);
+    std::fseek(f, sizeof(uint32_t), SEEK_SET);
+    B200_REQUIRE(bytes % (esz << w) == 0, "partition table size does not match the curve");
+    const size_t groups = bytes / (esz << w);
+    B200_REQUIRE(groups * w < (1ull << 31), "partition table too large");
+    std::vector<unsigned char> host(bytes);
+    B200_REQUIRE(bytes == 0 || std::fread(host.data(), bytes, 1, f) == 1, "short handle file");
+    std::fclose(f);
+    return reinterpret_cast<sxt_multiexp_handle*>(
+        handle_new(curve_id, host.data(), (unsigned)(groups * w), false, w, bytes));
+  }
+  B200_REQUIRE(std::fread(hdr + 1, 3 * sizeof(uint32_t), 1, f) == 1, "short handle file");
+  B200_REQUIRE(hdr[1] == 1u, "unsupported blitzar_b200 handle file version");
   B200_REQUIRE(hdr[2] == curve_id, "handle file is for another curve");
   size_t bytes = (size_t)hdr[3] * vt(curve_id).abi_proj_bytes;
   std::vector<unsigned char> host(bytes);

@@ -175,6 +175,16 @@ struct Ed25519 {
     F::canonical(g.T2d, g.T2d);
   }
 
+  // projective denominator of a point / generator form of the affine point (X zi, Y zi)
+  static B200_HD fe denominator(const Point& p) { return p.Z; }
+  static B200_HD void normalized_gen(Gen& g, const Point& p, const fe& zi) {
+    Point a;
+    F::mul(a.X, p.X, zi);
+    F::mul(a.Y, p.Y, zi);
+    a.Z = F::one();
+    F::mul(a.T, a.X, a.Y);
+    point_to_gen(g, a);
+  }
   // ---- FP64-pipe accumulator (see fp64field.cuh) --------------------------------------------------
   // Exact and parity-green on B200 (all GPU tests pass with it), but NOT faster: measured
   // (tests/micro/latency.cu) 82.8 SM-cycles per warp-multiplication against 82.9 for the integer
@@ -327,6 +337,18 @@ struct Ed25519 {
     point_to_gen(g, p);
   }
   static B200_HD void load_proj_abi(Gen& g, const void* src) { load_gen_abi(g, src); }
+  // c21t::compact_element {X, Y, T = XY} with Z = 1 (sxt/curve21/type/compact_element.h:30-38),
+  // the entry type of the reference's partition-table files
+  static constexpr int kAbiCompactBytes = 120;
+  static B200_HD void load_compact_abi(Gen& g, const void* src) {
+    const u64* s = (const u64*)src;
+    Point p;
+    F::from_radix51(p.X, s);
+    F::from_radix51(p.Y, s + 5);
+    p.Z = F::one();
+    F::from_radix51(p.T, s + 10);
+    point_to_gen(g, p);
+  }
   static B200_HD void store_proj_abi(void* dst, const Point& p) {
     u64* d = (u64*)dst;
     F::to_radix51(d, p.X);
@@ -619,6 +641,17 @@ template <class FieldT, class CP> struct Weierstrass {
     finish_add<X>(o, t0, t1, t3, t4, y3, z3);
     r = o;
   }
+  // projective denominator (1 for the identity, whose normalised form is the (0,0) generator)
+  static B200_HD fe denominator(const Point& p) { return F::is_zero(p.Z) ? F::one() : p.Z; }
+  static B200_HD void normalized_gen(Gen& g, const Point& p, const fe& zi) {
+    if (F::is_zero(p.Z)) {
+      g.x = F::zero();
+      g.y = F::zero();
+      return;
+    }
+    F::mul(g.x, p.X, zi);
+    F::mul(g.y, p.Y, zi);
+  }
   static B200_HD void gen_to_point(Point& r, const Gen& g, bool negate) {
     if (gen_is_identity(g)) {
       r = identity();
@@ -660,6 +693,19 @@ template <class FieldT, class CP> struct Weierstrass {
     }
     F::load(g.x, s);
     F::load(g.y, s + 4 * N);
+  }
+  // cg1t / cn1t / cgkt::compact_element {X, Y}; identity marked by an all-ones top limb of X
+  // (sxt/curve_g1/type/compact_element.h:31, curve_bng1/..., curve_gk/...)
+  static constexpr int kAbiCompactBytes = 8 * N;
+  static B200_HD void load_compact_abi(Gen& g, const void* src) {
+    const u32* s = (const u32*)src;
+    if ((s[N - 1] & s[N - 2]) == 0xffffffffu) {
+      g.x = F::zero();
+      g.y = F::zero();
+      return;
+    }
+    F::load(g.x, s);
+    F::load(g.y, s + N);
   }
   // projective ABI struct {X,Y,Z} -> affine generator (one field inversion)
   static B200_HD void load_proj_abi(Gen& g, const void* src) {

@@ -129,12 +129,22 @@ template <class C> struct CurveOps {
       cols[i].n = (u32)d[i].n;
       cols[i].is_signed = d[i].is_signed ? 1u : 0u;
       cols[i].first_window = cols[i].num_windows = 0;
+      cols[i].table_n = 0;
     }
     Point* pts = (Point*)out_partials;
     DevBuf<Point> tmp(out_partials ? 1 : num, s);
     if (!pts)
       pts = tmp.p;
-    run_columns(ctx, gens_ptr, cols, pts, num_ranges ? num_ranges : 1, &hook);
+    EngineCtx rctx = ctx;
+    // built-in generators covered by the precomputed fixed-base table (sxt_config::
+    // num_precomputed_generators): shared-bucket table mode when it is the cheaper run
+    if (n && !generators_dev && !hook.builtin &&
+        prefer_table(cols, ctx.builtin_window_bits, ctx.builtin_windows, ctx.opt)) {
+      rctx.opt.window_bits = ctx.builtin_window_bits;
+      for (auto& col : cols)
+        col.table_n = (u32)ctx.num_builtin;
+    }
+    run_columns(rctx, gens_ptr, cols, pts, num_ranges ? num_ranges : 1, &hook);
     if (out_commitments)
       launch(StoreBody<C, true>{pts, (unsigned char*)out_commitments}, num, s);
   }
@@ -169,13 +179,22 @@ template <class C> struct CurveOps {
       cols[j].n = len;
       cols[j].is_signed = 0;
       cols[j].first_window = cols[j].num_windows = 0;
+      cols[j].table_n = 0;
       bit_off += width;
     }
     Point* pts = (Point*)out_partials;
     DevBuf<Point> tmp(out_partials ? 1 : (num_outputs ? num_outputs : 1), s);
     if (!pts)
       pts = tmp.p;
-    run_columns(ctx, (const Gen*)h->gens, cols, pts);
+    if (prefer_table(cols, h->window_bits, h->windows, ctx.opt)) {
+      EngineCtx tctx = ctx;
+      tctx.opt.window_bits = h->window_bits;
+      for (auto& col : cols)
+        col.table_n = h->n;
+      run_columns(tctx, (const Gen*)h->gens, cols, pts);
+    } else {
+      run_columns(ctx, (const Gen*)h->gens, cols, pts);
+    }
     if (out_res)
       launch(StoreBody<C, false>{pts, (unsigned char*)out_res}, num_outputs, s);
   }
@@ -200,6 +219,50 @@ template <class C> struct CurveOps {
                         void* out_pts) {
     launch(SumPartsBody<C>{(const Point*)parts, nparts, count, (Point*)out_pts}, count, ctx.s);
   }
+  static void ingest_compact_table(const EngineCtx& ctx, const void* table_dev,
+                                   unsigned window_width, void* gens, uint64_t n) {
+    launch(IngestCompactBody<C>{(const unsigned char*)table_dev, window_width, (Gen*)gens}, n,
+           ctx.s);
+  }
+  static void build_table(const EngineCtx& ctx, void* table, uint64_t n, unsigned window_bits,
+                          unsigned windows) {
+    B200_REQUIRE(windows <= (unsigned)kMaxTableWindows, "too many table windows");
+    if (windows > 1)
+      launch(PrecomputeTableBody<C>{(Gen*)table, n, window_bits, windows}, n, ctx.s);
+  }
+  // Table mode pays when the shared-bucket run (digit additions + ONE bucket reduction per column)
+  // is cheaper than the variable-base run at the window width that run would choose; many short
+  // columns (bucket_method2-style shapes) stay on the variable-base path.
+  static bool prefer_table(const std::vector<ColumnDesc>& cols, unsigned table_c,
+                           unsigned table_windows, const MsmOptions& opt) {
+    if (table_windows <= 1 || table_c == 0)
+      return false;
+    u64 max_n = 0;
+    u32 max_width = 1, ncols = 0;
+    for (auto& col : cols)
+      if (col.n) {
+        max_n = std::max<u64>(max_n, col.n);
+        max_width = std::max(max_width, col.bit_width);
+        ++ncols;
+      }
+    if (ncols == 0 || max_width / table_c + 1 > table_windows || opt.table_policy == 2)
+      return false;
+    if (opt.table_policy == 1)
+      return true;
+    const double nb_t = (double)(1u << (table_c - 1));
+    if ((double)ncols * nb_t * (double)sizeof(Point) > 3.0e9)
+      return false;
+    const u32 cv = opt.window_bits ? opt.window_bits
+                                   : choose_window_bits(max_n, max_width, ncols, sizeof(Point));
+    const double nb_v = (double)(1u << (cv - 1));
+    double cost_t = 0, cost_v = 0;
+    for (auto& col : cols)
+      if (col.n) {
+        cost_t += (double)col.n * (col.bit_width / table_c + 1) + 2.5 * nb_t;
+        cost_v += (double)(col.bit_width / cv + 1) * ((double)col.n + 2.5 * nb_v);
+      }
+    return cost_t < cost_v;
+  }
   static void synth_generators(const EngineCtx& ctx, void* out_dev, uint64_t n, uint64_t first,
                                bool projective) {
     Synth<C>::generators(ctx.s, out_dev, n, first, projective);
@@ -219,6 +282,9 @@ template <class C> struct CurveOps {
                             &CurveOps<C>::gens_to_projective,                                      \
                             &CurveOps<C>::store,                                                   \
                             &CurveOps<C>::sum_parts,                                               \
-                            &CurveOps<C>::synth_generators}
+                            &CurveOps<C>::synth_generators,                                        \
+                            (unsigned)C::kAbiCompactBytes,                                         \
+                            &CurveOps<C>::ingest_compact_table,                                    \
+                            &CurveOps<C>::build_table}
 
 }  // namespace b200

@@ -18,6 +18,7 @@ struct MsmOptions {
   u64 max_group_entries = 1ull << 30;  // columns are grouped below this many (term, window) entries
   u64 max_range_entries = 1ull << 31;  // one sort pass holds at most this many entries: longer
                                        // columns are processed as several generator ranges
+  u32 table_policy = 0;  // fixed-base tables: 0 = cost model decides, 1 = whenever available, 2 = never
 };
 
 struct EngineCtx {
@@ -26,13 +27,41 @@ struct EngineCtx {
   const void* builtin;  // device-resident built-in ristretto generators g(0..num_builtin)
   uint64_t num_builtin;
   stream_t tail = stream_t();  // optional second stream: cascade + merge of piece k under piece k+1
+  // fixed-base table over the built-in generators (window w of generator i at builtin[w n + i]);
+  // builtin_windows <= 1: plain generators only
+  u32 builtin_window_bits = 0, builtin_windows = 0;
 };
 
+// sxt_multiexp_handle: generators of one curve resident in HBM, plus (when it pays and fits) the
+// fixed-base table 2^(c w) G_i, w < windows, laid out window-major: entry w * n + i. Window 0 IS the
+// generator array, so `gens` serves both the table mode and the variable-base fallback.
 struct Handle {
   unsigned curve_id;
   unsigned n;
-  void* gens;  // device array of the curve's generator layout
+  void* gens;  // device array of the curve's generator layout, windows * n entries
+  unsigned window_bits = 0, windows = 1;
 };
+
+// Window width of a fixed-base table over n generators: minimises (digit additions + bucket
+// reduction) for one 256-bit output, subject to the table fitting in `budget_bytes` and in the
+// 31-bit generator index of a sorted entry. Returns 0 when no table should be built.
+inline unsigned table_window_bits(uint64_t n, size_t gen_bytes, double budget_bytes) {
+  if (n < 1024)  // tiny handles: the variable-base path with a small window wins anyway
+    return 0;
+  unsigned best = 0;
+  double best_cost = 1e300;
+  for (unsigned c = 10; c <= 20; ++c) {
+    const double W = 256 / c + 1;
+    if (W * (double)n * (double)gen_bytes > budget_bytes || W * (double)n >= 2147483648.0)
+      continue;
+    const double cost = W * (double)n + 2.5 * (double)(1u << (c - 1));
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = c;
+    }
+  }
+  return best;
+}
 
 template <class T> struct DevBuf {
   T* p = nullptr;
@@ -70,6 +99,13 @@ struct CurveVTable {
   // synthetic generators (synth.cuh) in the ABI layout: projective structs or commit-stride affine
   void (*synth_generators)(const EngineCtx&, void* out_dev, uint64_t n, uint64_t first,
                            bool projective);
+  unsigned abi_compact_bytes;
+  // generators out of a reference partition-table image (device copy of the file's table)
+  void (*ingest_compact_table)(const EngineCtx&, const void* table_dev, unsigned window_width,
+                               void* gens, uint64_t n);
+  // fills windows 1 .. windows-1 of a fixed-base table whose window 0 (n generators) is in place
+  void (*build_table)(const EngineCtx&, void* table, uint64_t n, unsigned window_bits,
+                      unsigned windows);
 };
 extern const CurveVTable kVTableEd25519, kVTableBls12381, kVTableBn254, kVTableGrumpkin;
 

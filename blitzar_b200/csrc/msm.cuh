@@ -37,8 +37,15 @@ struct ColumnDesc {
   u32 n;
   u32 is_signed;
   u32 first_window;
-  u32 num_windows;
+  u32 num_windows;  // digit windows of the column
+  // Fixed-base table mode (generators come from a precomputed table of 2^(c w) G_i, w-major with
+  // stride table_n): the digit of window w addresses generator w * table_n + i and ALL windows of the
+  // column share ONE bucket set (first_window), so there is no Horner tail. 0 = one bucket set per
+  // window (variable-base).
+  u32 table_n;
+  u32 reserved_;
 };
+B200_HD u32 bucket_windows(const ColumnDesc& col) { return col.table_n ? (col.num_windows ? 1u : 0u) : col.num_windows; }
 
 B200_HD void load_scalar_bits(u32 v[8], bool& negative, const ColumnDesc& col, u64 i) {
   const unsigned char* row = col.base + i * col.row_stride;
@@ -111,7 +118,7 @@ B200_HD void load_scalar_bits(u32 v[8], bool& negative, const ColumnDesc& col, u
   }
 }
 
-// Signed c-bit digit recoding; calls f(key, negate) for every non-zero digit.
+// Signed c-bit digit recoding; calls f(key, negate, window) for every non-zero digit.
 template <class Fn>
 B200_HD void for_each_digit(const u32 v[8], bool negative, const ColumnDesc& col, u32 c,
                             u32 nbuckets, Fn f) {
@@ -133,7 +140,7 @@ B200_HD void for_each_digit(const u32 v[8], bool negative, const ColumnDesc& col
       if (dneg)
         d = (1u << c) - d;
       if (d)
-        f((col.first_window + w) * nbuckets + (d - 1u), negative != dneg);
+        f((col.first_window + (col.table_n ? 0u : w)) * nbuckets + (d - 1u), negative != dneg, w);
       ++w;
     }
   }
@@ -145,7 +152,7 @@ B200_HD void for_each_digit(const u32 v[8], bool negative, const ColumnDesc& col
     if (dneg)
       d = (1u << c) - d;
     if (d)
-      f((col.first_window + w) * nbuckets + (d - 1u), negative != dneg);
+      f((col.first_window + (col.table_n ? 0u : w)) * nbuckets + (d - 1u), negative != dneg, w);
     ++w;
   }
 }
@@ -178,7 +185,7 @@ struct CountBody {
     bool neg;
     load_scalar_bits(v, neg, col, i);
     u32* cnt = counts;
-    for_each_digit(v, neg, col, c, nbuckets, [cnt](u32 key, bool) { B200_ATOMIC_ADD(&cnt[key], 1u); });
+    for_each_digit(v, neg, col, c, nbuckets, [cnt](u32 key, bool, u32) { B200_ATOMIC_ADD(&cnt[key], 1u); });
   }
 };
 
@@ -198,10 +205,10 @@ struct ScatterBody {
     load_scalar_bits(v, neg, col, i);
     u32* cur = cursor;
     u64* en = entries;
-    u32 ii = (u32)i;
-    for_each_digit(v, neg, col, c, nbuckets, [cur, en, ii](u32 key, bool negate) {
+    const u32 ii = (u32)i, tn = col.table_n;
+    for_each_digit(v, neg, col, c, nbuckets, [cur, en, ii, tn](u32 key, bool negate, u32 w) {
       u32 pos = B200_ATOMIC_ADD(&cur[key], 1u);
-      en[pos] = ((u64)key << 32) | (u64)((ii << 1) | (negate ? 1u : 0u));
+      en[pos] = ((u64)key << 32) | (u64)(((ii + w * tn) << 1) | (negate ? 1u : 0u));
     });
   }
 };
@@ -529,8 +536,9 @@ template <class C, class X = SeqExec> struct CombineBody {
         out[j] = C::identity();
       return;
     }
-    Point acc = S[col.first_window + col.num_windows - 1];
-    for (u32 w = col.num_windows - 1; w-- > 0;) {
+    const u32 nw = bucket_windows(col);  // table mode: one shared bucket set, no Horner
+    Point acc = S[col.first_window + nw - 1];
+    for (u32 w = nw - 1; w-- > 0;) {
       for (u32 i = 0; i < c; ++i)
         C::template dbl<X>(acc, acc);
       C::template add<X>(acc, acc, S[col.first_window + w]);
@@ -551,6 +559,57 @@ template <class C, bool kProjective> struct IngestBody {
       C::load_proj_abi(g, raw + i * C::kAbiProjBytes);
     else
       C::load_gen_abi(g, raw + i * C::kAbiGenBytes);
+    gens[i] = g;
+  }
+};
+// Fixed-base precomputation (replaces mtxpp2::compute_partition_table, sxt/multiexp/pippenger2/
+// partition_table.h:36-98 — the reference tabulates all 2^w subset sums of w-generator groups; here
+// the table holds 2^(c w) G_i for every window w, normalised to Z = 1, so that all windows of a
+// fixed-base MSM share one bucket set and the Horner tail disappears). table[0 .. n) holds the
+// generators on entry; thread i fills table[w n + i], w = 1 .. W-1, with one inversion
+// (Montgomery's trick over its W-1 points).
+constexpr int kMaxTableWindows = 33;  // c >= 8
+template <class C> struct PrecomputeTableBody {
+  static constexpr int kBlock = 64;
+  typename C::Gen* table;
+  u64 n;
+  u32 c, W;
+  B200_HD void operator()(u64 i) const {
+    typedef typename C::F F;
+    typename C::Point p, pts[kMaxTableWindows];
+    typename F::E prefix[kMaxTableWindows], acc = F::one(), inv;
+    C::gen_to_point(p, table[i], false);
+    for (u32 w = 1; w < W; ++w) {
+      for (u32 k = 0; k < c; ++k)
+        C::dbl(p, p);
+      pts[w] = p;
+      prefix[w] = acc;
+      F::mul(acc, acc, C::denominator(p));
+    }
+    F::invert(inv, acc);
+    for (u32 w = W - 1; w >= 1; --w) {
+      typename F::E zi;
+      F::mul(zi, inv, prefix[w]);
+      F::mul(inv, inv, C::denominator(pts[w]));
+      typename C::Gen g;
+      C::normalized_gen(g, pts[w], zi);
+      table[(u64)w * n + i] = g;
+    }
+  }
+};
+// generators out of a reference partition-table file: entry (1 << j) of group g is generator
+// g * w + j (mtxpp2::in_memory_partition_table_accessor::copy_generators,
+// sxt/multiexp/pippenger2/in_memory_partition_table_accessor.h:68-81)
+template <class C> struct IngestCompactBody {
+  static constexpr int kBlock = 128;
+  const unsigned char* table;  // the file's table (device copy)
+  u32 window_width;
+  typename C::Gen* gens;
+  B200_HD void operator()(u64 i) const {
+    const u64 group = i / window_width, j = i % window_width;
+    const u64 entry = (group << window_width) + (1ull << j);
+    typename C::Gen g;
+    C::load_compact_abi(g, table + entry * C::kAbiCompactBytes);
     gens[i] = g;
   }
 };
@@ -648,8 +707,10 @@ inline MsmPlan msm_make_plan(std::vector<ColumnDesc> cols, const MsmOptions& opt
   for (auto& col : cols) {
     col.first_window = p.total_windows;
     col.num_windows = col.n ? col.bit_width / p.c + 1 : 0;
-    p.total_windows += col.num_windows;
+    p.total_windows += bucket_windows(col);
     max_entries += (u64)col.n * col.num_windows;
+    if (col.table_n)
+      B200_REQUIRE((u64)col.table_n * col.num_windows < (1ull << 31), "generator table too large");
   }
   p.nkeys = (u64)p.total_windows * p.nbuckets;
   p.total_entries = max_entries;
@@ -827,7 +888,7 @@ void msm_finish(stream_t s, const MsmPlan& plan, const typename C::Point* d_buck
     dev_free(ptr, s);
   bool uniform_windows = true;  // same Horner trip count in every quad of a warp
   for (u32 j = 1; j < ncols; ++j)
-    uniform_windows = uniform_windows && plan.cols[j].num_windows == plan.cols[0].num_windows;
+    uniform_windows = uniform_windows && bucket_windows(plan.cols[j]) == bucket_windows(plan.cols[0]);
   if (ncols <= opt.quad_threshold && uniform_windows)
     launch(CombineBody<C, QuadExecConv>{d_S, d_cols, plan.c, out}, (u64)ncols * QuadExec::kLanes,
            s);

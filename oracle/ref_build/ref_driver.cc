@@ -284,7 +284,40 @@ static void fixed_impl(void* res, const void* generators, unsigned num_generator
   }
 }
 
+// The reference's partition-table file of a handle (sxt_multiexp_handle_write_to_file ->
+// in_memory_partition_table_accessor::write_to_file, in_memory_partition_table_accessor.h:98-105):
+// [u32 window_width][table of compact elements].
+template <class U, class T>
+static void write_table_impl(const char* filename, const void* generators, unsigned num_generators,
+                             unsigned window_width) {
+  auto accessor = mtxpp2::make_in_memory_partition_table_accessor<U, T>(
+      basct::cspan<T>{static_cast<const T*>(generators), num_generators}, basm::alloc_t{},
+      window_width);
+  accessor->write_to_file(filename);
+}
+
 extern "C" {
+void ref_write_partition_table(unsigned curve_id, const char* filename, const void* generators,
+                               unsigned num_generators, unsigned window_width) {
+  switch (curve_id) {
+  case 0:
+    write_table_impl<c21t::compact_element, c21t::element_p3>(filename, generators, num_generators,
+                                                              window_width);
+    break;
+  case 1:
+    write_table_impl<cg1t::compact_element, cg1t::element_p2>(filename, generators, num_generators,
+                                                              window_width);
+    break;
+  case 2:
+    write_table_impl<cn1t::compact_element, cn1t::element_p2>(filename, generators, num_generators,
+                                                              window_width);
+    break;
+  default:
+    write_table_impl<cgkt::compact_element, cgkt::element_p2>(filename, generators, num_generators,
+                                                              window_width);
+    break;
+  }
+}
 void ref_fixed_msm(unsigned curve_id, void* res, const void* generators, unsigned num_generators,
                    unsigned window_width, int mode, unsigned element_num_bytes,
                    const unsigned* output_bit_table, const unsigned* output_lengths,

@@ -109,6 +109,14 @@ def fixed_msm(curve_id, generators_p, num_outputs, n, scalars, element_num_bytes
     return res
 
 
+def write_partition_table(curve_id, filename, generators_p, window_width):
+    """The reference's handle file ([u32 window_width][partition table]) for these generators."""
+    generators_p = np.ascontiguousarray(generators_p, dtype=np.uint8)
+    lib().ref_write_partition_table(C.c_uint(curve_id), filename.encode(),
+                                    C.c_void_p(generators_p.ctypes.data),
+                                    C.c_uint(generators_p.shape[0]), C.c_uint(window_width))
+
+
 # ---- inner-product argument (reference cpu backend; cbindings/inner_product_proof.cc) -------------
 def transcript_new(label=b"ip-test"):
     t = np.zeros(203, dtype=np.uint8)

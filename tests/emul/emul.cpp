@@ -25,9 +25,38 @@ static const CurveVTable& vt(unsigned curve_id) {
 
 static MsmOptions g_opt;
 static unsigned g_ranges = 1;
+static unsigned g_table_c = 0;  // fixed-base table window of emul_fixed handles (0 = no table)
+static std::vector<unsigned char> g_builtin;  // built-in generator table of emul_commit
+static uint64_t g_num_builtin = 0;
+static unsigned g_builtin_c = 0;
+static EngineCtx make_ctx() {
+  EngineCtx ctx{0, g_opt, g_builtin.empty() ? nullptr : g_builtin.data(), g_num_builtin};
+  ctx.builtin_window_bits = g_builtin_c;
+  ctx.builtin_windows = g_builtin_c ? 256 / g_builtin_c + 1 : (g_num_builtin ? 1 : 0);
+  return ctx;
+}
 
 extern "C" {
 void emul_set_ranges(unsigned num_ranges) { g_ranges = num_ranges ? num_ranges : 1; }
+void emul_set_table(unsigned window_bits, unsigned policy) {
+  g_table_c = window_bits;
+  g_opt.table_policy = policy;
+}
+// sxt_config::num_precomputed_generators with a fixed-base table of the given window (0 = none)
+void emul_set_builtin(uint64_t np, unsigned window_bits) {
+  g_builtin.clear();
+  g_num_builtin = 0;
+  g_builtin_c = 0;
+  if (np == 0) return;
+  const unsigned windows = window_bits ? 256 / window_bits + 1 : 1;
+  std::vector<unsigned char> t((size_t)np * windows * vt(0).gen_bytes);
+  EngineCtx ctx{0, g_opt, nullptr, 0};
+  launch_builtin_generators(ctx, t.data(), 0, np);
+  vt(0).build_table(ctx, t.data(), np, window_bits, windows);
+  g_builtin.swap(t);
+  g_num_builtin = np;
+  g_builtin_c = window_bits;
+}
 void emul_set_range_entries(unsigned long long v) { g_opt.max_range_entries = v ? v : (1ull << 31); }
 void emul_set_group_entries(unsigned long long v) { g_opt.max_group_entries = v ? v : (1ull << 30); }
 void emul_set_tuning(unsigned window_bits, unsigned chunk1, unsigned chunkn) {
@@ -39,30 +68,43 @@ void emul_set_tuning(unsigned window_bits, unsigned chunk1, unsigned chunkn) {
 void emul_commit(unsigned curve_id, void* out_commitments, uint32_t num,
                  const sxt_sequence_descriptor* d, const void* generators, uint64_t offset) {
   if (num == 0) return;
-  EngineCtx ctx{0, g_opt, nullptr, 0};
+  EngineCtx ctx = make_ctx();
   vt(curve_id).commit_device(ctx, out_commitments, nullptr, num, d, generators, offset, g_ranges,
                              nullptr, nullptr);
 }
 void emul_get_generators(void* out160, uint64_t num, uint64_t offset) {
-  EngineCtx ctx{0, g_opt, nullptr, 0};
+  EngineCtx ctx = make_ctx();
   std::vector<unsigned char> g((num ? num : 1) * vt(0).gen_bytes);
   launch_builtin_generators(ctx, g.data(), offset, num);
   vt(0).gens_to_projective(ctx, g.data(), out160, num);
 }
 // same contract as b200_synthetic_generators_device (host memory)
 void emul_synth_generators(unsigned curve_id, void* out, uint64_t n, uint64_t first, int projective) {
-  EngineCtx ctx{0, g_opt, nullptr, 0};
+  EngineCtx ctx = make_ctx();
   vt(curve_id).synth_generators(ctx, out, n, first, projective != 0);
+}
+// generators recovered from a reference partition-table image, as projective ABI structs
+void emul_ingest_compact(unsigned curve_id, const void* table, unsigned window_width, uint64_t n,
+                         void* out_proj) {
+  EngineCtx ctx = make_ctx();
+  const CurveVTable& V = vt(curve_id);
+  std::vector<unsigned char> gens((size_t)(n ? n : 1) * V.gen_bytes);
+  V.ingest_compact_table(ctx, table, window_width, gens.data(), n);
+  V.gens_to_projective(ctx, gens.data(), out_proj, n);
 }
 // handle_new + fixed MSM in one call (mode as in b200_fixed_msm_device)
 void emul_fixed(unsigned curve_id, void* res, const void* generators_proj, unsigned num_gens,
                 int mode, unsigned element_num_bytes, const unsigned* bit_table,
                 const unsigned* lengths, unsigned num_outputs, unsigned n, const uint8_t* scalars) {
-  EngineCtx ctx{0, g_opt, nullptr, 0};
+  EngineCtx ctx = make_ctx();
   const CurveVTable& V = vt(curve_id);
-  std::vector<unsigned char> gens((size_t)(num_gens ? num_gens : 1) * V.gen_bytes);
+  const unsigned windows = g_table_c ? 256 / g_table_c + 1 : 1;
+  std::vector<unsigned char> gens((size_t)(num_gens ? num_gens : 1) * windows * V.gen_bytes);
   V.ingest_projective(ctx, generators_proj, gens.data(), num_gens);
+  V.build_table(ctx, gens.data(), num_gens, g_table_c, windows);
   Handle h{curve_id, num_gens, gens.data()};
+  h.window_bits = g_table_c;
+  h.windows = windows;
   unsigned rows = n;
   if (mode == 2) {
     rows = 0;
@@ -144,13 +186,13 @@ extern "C" void emul_commit_partial(unsigned curve_id, void* out_partials, uint3
                                     const sxt_sequence_descriptor* d, const void* generators,
                                     uint64_t offset) {
   if (num == 0) return;
-  EngineCtx ctx{0, g_opt, nullptr, 0};
+  EngineCtx ctx = make_ctx();
   vt(curve_id).commit_device(ctx, nullptr, out_partials, num, d, generators, offset, g_ranges,
                              nullptr, nullptr);
 }
 extern "C" void emul_combine_partials(unsigned curve_id, void* out_commitments, const void* partials,
                                       uint32_t num_parts, uint32_t count) {
-  EngineCtx ctx{0, g_opt, nullptr, 0};
+  EngineCtx ctx = make_ctx();
   const CurveVTable& V = vt(curve_id);
   std::vector<unsigned char> sum((size_t)count * V.point_bytes);
   V.sum_parts(ctx, partials, num_parts, count, sum.data());
@@ -204,14 +246,14 @@ extern "C" int emul_check_fp64(unsigned iters, unsigned seed) {
 extern "C" void emul_prove_inner_product(uint8_t* l_vector, uint8_t* r_vector, uint8_t* ap_value,
                                          uint8_t* transcript203, uint64_t n, uint64_t offset,
                                          const uint8_t* a_vector, const uint8_t* b_vector) {
-  EngineCtx ctx{0, g_opt, nullptr, 0};
+  EngineCtx ctx = make_ctx();
   ipa_prove(ctx, l_vector, r_vector, ap_value, transcript203, n, offset, a_vector, b_vector);
 }
 extern "C" int emul_verify_inner_product(uint8_t* transcript203, uint64_t n, uint64_t offset,
                                          const uint8_t* b_vector, const uint8_t* product,
                                          const uint8_t* a_commit160, const uint8_t* l_vector,
                                          const uint8_t* r_vector, const uint8_t* ap_value) {
-  EngineCtx ctx{0, g_opt, nullptr, 0};
+  EngineCtx ctx = make_ctx();
   return ipa_verify(ctx, transcript203, n, offset, b_vector, product, a_commit160, l_vector,
                     r_vector, ap_value);
 }

@@ -65,6 +65,15 @@ def set_group_entries(v=0):
     lib().emul_set_group_entries(C.c_ulonglong(v))
 
 
+def set_table(window_bits=0, policy=0):
+    """fixed-base table of emul_fixed handles; policy 1 = always use it, 2 = never, 0 = cost model"""
+    lib().emul_set_table(C.c_uint(window_bits), C.c_uint(policy))
+
+
+def set_builtin(num_precomputed=0, window_bits=0):
+    lib().emul_set_builtin(C.c_uint64(num_precomputed), C.c_uint(window_bits))
+
+
 def set_ranges(num_ranges=1):
     lib().emul_set_ranges(C.c_uint(num_ranges))
 
@@ -162,4 +171,18 @@ def synth_generators(curve_id, n, first=0, projective=False):
     out = np.zeros((n, stride), dtype=np.uint8)
     lib().emul_synth_generators(C.c_uint(curve_id), C.c_void_p(out.ctypes.data), C.c_uint64(n),
                                 C.c_uint64(first), C.c_int(1 if projective else 0))
+    return out
+
+
+def generators_from_reference_table(curve_id, path):
+    """Generators (projective ABI structs) recovered from a reference-format handle file."""
+    raw = np.fromfile(path, dtype=np.uint8)
+    w = int(raw[:4].view("<u4")[0])
+    esz = {0: 120, 1: 96, 2: 64, 3: 64}[curve_id]
+    groups = (raw.size - 4) // (esz << w)
+    n = groups * w
+    table = np.ascontiguousarray(raw[4:])
+    out = np.zeros((n, SIZES[curve_id][0]), dtype=np.uint8)
+    lib().emul_ingest_compact(C.c_uint(curve_id), C.c_void_p(table.ctypes.data), C.c_uint(w),
+                              C.c_uint64(n), C.c_void_p(out.ctypes.data))
     return out

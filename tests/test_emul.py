@@ -191,3 +191,66 @@ def test_long_columns_split_into_sort_passes(emul, port):
     finally:
         emul.set_range_entries(0)
     assert common.same(2, got, port.commit(2, cols, gens))
+
+
+# ---- fixed-base tables (2^(c w) G_i, shared bucket set) ----------------------------------------------
+@pytest.mark.parametrize("curve", [0, 2])
+@pytest.mark.parametrize("window_bits", [10, 16, 19])
+def test_fixed_base_table_mode(emul, port, curve, window_bits):
+    """Replaces mtxpp2's partition table (sxt/multiexp/pippenger2/partition_table.h:36-98): every
+    window's multiple of every generator is tabulated, all windows share one bucket set. Same results
+    as the oracle for fixed-width, packed and variable-length calls."""
+    rng = np.random.default_rng(40 + curve + window_bits)
+    m = 400
+    _, gens_p = common.generators_for(port, curve, m)
+    try:
+        emul.set_table(window_bits, 1)
+        sc = rng.integers(0, 256, (m, 2 * 32), dtype=np.uint8)
+        a = emul.fixed_msm(curve, gens_p, 2, m, sc, element_num_bytes=32)
+        b = port.fixed_msm(curve, gens_p, 2, m, sc, element_num_bytes=32)
+        assert common.same(curve, port.normalize(curve, a), port.normalize(curve, b))
+        bt = [3, 1, 14, 9, 64, 5, 200]
+        psc = rng.integers(0, 256, (m, (sum(bt) + 7) // 8), dtype=np.uint8)
+        lens = [1, 2, 17, 17, 40, 50, 400]
+        a = emul.fixed_msm(curve, gens_p, len(bt), m, psc, output_bit_table=bt, output_lengths=lens)
+        b = port.fixed_msm(curve, gens_p, len(bt), m, psc, output_bit_table=bt, output_lengths=lens)
+        assert common.same(curve, port.normalize(curve, a), port.normalize(curve, b))
+        emul.set_table(window_bits, 0)  # cost model: short columns fall back to the variable-base run
+        a = emul.fixed_msm(curve, gens_p, len(bt), m, psc, output_bit_table=bt)
+        b = port.fixed_msm(curve, gens_p, len(bt), m, psc, output_bit_table=bt)
+        assert common.same(curve, port.normalize(curve, a), port.normalize(curve, b))
+    finally:
+        emul.set_table(0, 0)
+
+
+def test_builtin_generator_table(emul, port):
+    """sxt_config::num_precomputed_generators with the fixed-base table: commitments over the built-in
+    generators inside, straddling and beyond the table."""
+    rng = np.random.default_rng(77)
+    cols = common.random_columns(rng, 300, [(0, 32, 0), (-100, 16, 1), (0, 1, 0), (-299, 8, 0)])
+    try:
+        for c in (0, 12):
+            emul.set_builtin(400, c)
+            emul.set_table(0, 1 if c else 0)
+            for off in (0, 37, 100, 250):
+                assert np.array_equal(emul.commit(0, cols, None, off), port.commit(0, cols, None, off))
+    finally:
+        emul.set_builtin(0, 0)
+        emul.set_table(0, 0)
+
+
+@pytest.mark.parametrize("curve", [0, 1, 2, 3])
+def test_generators_from_reference_partition_table_file(emul, port, curve):
+    """tests/golden/ref_table_curve{c}_w3.bin was written by the reference's own code (oracle/_ref,
+    tests/golden/make_table_files.py) for 7 generators; the reader recovers them (padded with
+    identities to a multiple of the window width)."""
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    want = np.load(os.path.join(here, f"fixed_curve{curve}.npz"))["generators_p"][:7]
+    got = emul.generators_from_reference_table(curve, os.path.join(here, f"ref_table_curve{curve}_w3.bin"))
+    assert got.shape[0] == 9
+    assert common.same(curve, port.normalize(curve, got[:7]), port.normalize(curve, want))
+    ident = port.normalize(curve, got[7:])
+    zero = port.commit(curve, [(np.zeros((0, 4), dtype=np.uint8), 0)] * 2,
+                       common.generators_for(port, curve, 1)[0])
+    assert common.same(curve, ident, zero)

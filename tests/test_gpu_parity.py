@@ -278,3 +278,78 @@ def test_columns_split_over_devices(bb):
     r = subprocess.run([sys.executable, "-c", _MULTI_DEVICE_SCRIPT, root], env=env, cwd=root,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "multi-device ok" in r.stdout, r.stdout + r.stderr
+
+
+# ---- fixed-base tables --------------------------------------------------------------------------------
+@pytest.mark.parametrize("curve", [0, 1, 2, 3])
+def test_fixed_base_table_policies_agree(bb, port, curve, monkeypatch):
+    """A handle holds the table 2^(c w) G_i; the same calls with the table forced on, forced off and
+    under the cost model give the oracle's results (window width from the environment override)."""
+    rng = np.random.default_rng(90 + curve)
+    m = 3000
+    _, gens_p = common.generators_for(port, curve, m)
+    sc = rng.integers(0, 256, (m, 2 * 32), dtype=np.uint8)
+    want = port.normalize(curve, port.fixed_msm(curve, gens_p, 2, m, sc, element_num_bytes=32))
+    bt = [3, 1, 14, 64, 5, 200]
+    psc = rng.integers(0, 256, (m, (sum(bt) + 7) // 8), dtype=np.uint8)
+    lens = [1, 2, 17, 40, 50, m]
+    wantv = port.normalize(curve, port.fixed_msm(curve, gens_p, len(bt), m, psc, output_bit_table=bt,
+                                                 output_lengths=lens))
+    for window in ("10", "16", "20", None):
+        if window:
+            monkeypatch.setenv("BLITZAR_B200_TABLE_WINDOW", window)
+        else:
+            monkeypatch.delenv("BLITZAR_B200_TABLE_WINDOW")
+        h = bb.MultiexpHandle(curve, gens_p)
+        for policy in ("1", "2", "0"):
+            monkeypatch.setenv("BLITZAR_B200_TABLE_POLICY", policy)
+            got = h.fixed_multiexponentiation(32, 2, m, sc)
+            assert common.same(curve, port.normalize(curve, got), want), (window, policy)
+            got = h.fixed_vlen_multiexponentiation(bt, lens, psc)
+            assert common.same(curve, port.normalize(curve, got), wantv), (window, policy)
+        h.free()
+    monkeypatch.delenv("BLITZAR_B200_TABLE_POLICY")
+
+
+@pytest.mark.parametrize("curve", [0, 1, 2, 3])
+def test_handle_from_reference_partition_table_file(bb, port, curve):
+    """sxt_multiexp_handle_new_from_file reads the reference's own [u32 w][partition table] files
+    (fixture written by the reference's code, tests/golden/make_table_files.py)."""
+    gens_p = np.load(os.path.join(GOLDEN_DIR, f"fixed_curve{curve}.npz"))["generators_p"][:7]
+    h = bb.MultiexpHandle(curve, filename=os.path.join(GOLDEN_DIR, f"ref_table_curve{curve}_w3.bin"))
+    rng = np.random.default_rng(curve)
+    sc = rng.integers(0, 256, (7, 32), dtype=np.uint8)
+    got = h.fixed_multiexponentiation(32, 1, 7, sc)
+    want = port.fixed_msm(curve, gens_p, 1, 7, sc, element_num_bytes=32)
+    assert common.same(curve, port.normalize(curve, got), port.normalize(curve, want))
+    h.free()
+
+
+def test_builtin_generator_table_subprocess():
+    """num_precomputed_generators large enough for a fixed-base table over the built-in generators:
+    commitments inside, straddling and beyond it, table forced on / off / cost model."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = r'''
+import sys, os, numpy as np
+sys.path.insert(0, sys.argv[1])
+import blitzar_b200.api as bb
+from oracle import port
+from tests import common
+port.build()
+assert bb.sxt_init(num_precomputed_generators=5000) == 0
+rng = np.random.default_rng(3)
+cols = common.random_columns(rng, 4000, [(0, 32, 0), (-100, 16, 1), (0, 1, 0), (-3999, 8, 0)])
+for policy in ("1", "2", "0"):
+    os.environ["BLITZAR_B200_TABLE_POLICY"] = policy
+    for off in (0, 37, 1000, 4000):
+        assert np.array_equal(bb.compute_pedersen_commitments(0, cols, None, off),
+                              port.commit(0, cols, None, off)), (policy, off)
+g = bb.get_generators(10, 4995)
+assert np.array_equal(port.normalize(0, g), port.normalize(0, port.ristretto_generators(10, 4995)))
+print("builtin table ok")
+'''
+    r = subprocess.run([sys.executable, "-c", script, root], cwd=root, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and "builtin table ok" in r.stdout, r.stdout + r.stderr
