@@ -252,8 +252,8 @@ def run_workload(env, name, scaling, steps, warmup, with_e2e=True, sampler=None)
     gen_stride = {0: 160, 1: 104, 2: 72, 3: 72}[curve]
     proj_stride = {0: 160, 1: 144, 2: 96, 3: 96}[curve]
     out_bytes = {0: 32, 1: 48, 2: 72, 3: 72}[curve]
-    fixed = name == "c5"
-    by_column = name == "c4"
+    fixed = name.startswith("c5")
+    by_column = name.startswith("c4")
     if by_column:  # columns are sharded; every rank holds all generators
         assert ncol_total % world == 0
         ncol, n, first = ncol_total // world, n_cfg, 0

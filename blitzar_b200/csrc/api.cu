@@ -52,6 +52,10 @@ EngineCtx ctx_of(const State& st) {
     c.tail = st.tail_stream;
   if (const char* env = std::getenv("BLITZAR_B200_GROUP_ENTRIES"))  // test hook: force column groups
     c.opt.max_group_entries = std::strtoull(env, nullptr, 10);
+  if (const char* env = std::getenv("BLITZAR_B200_PAIR_LEVELS"))  // batch-affine levels (-1 = auto)
+    c.opt.pair_levels = std::atoi(env);
+  if (const char* env = std::getenv("BLITZAR_B200_PAIR_BATCH"))
+    c.opt.pair_batch = (u32)std::atoi(env);
   if (const char* env = std::getenv("BLITZAR_B200_TABLE_POLICY"))  // 1 = always use tables, 2 = never
     c.opt.table_policy = (u32)std::atoi(env);
   return c;
@@ -309,6 +313,7 @@ void commit_on(const State& st, unsigned curve_id, void* commitments, uint32_t n
                const sxt_sequence_descriptor* d, const void* generators,
                uint64_t offset_generators, void* out_partials_dev = nullptr) {
   const CurveVTable& V = vt(curve_id);
+  StageRange nvtx("commit (host buffers)");
   cudaStream_t s = st.stream, sc = st.copy_stream;
   uint64_t n = longest_column(d, num);
   size_t total_scalar_bytes = 0;
@@ -367,6 +372,9 @@ void commit_on(const State& st, unsigned curve_id, void* commitments, uint32_t n
     B200_CUDA(cudaEventRecord(st.range_events[r], sc));
     mark(sc);
   };
+  B200_LOG(2, "commit: curve %u, %u columns, n = %llu, device %d, %u upload pieces, generators %s",
+           curve_id, num, (unsigned long long)n, st.device, num_ranges,
+           generators ? "from the caller" : "built in");
   RangeWaitState w{n, num_ranges, &st, 0, upload};
   V.commit_device(ctx_of(st), out_partials_dev ? nullptr : out.p, out_partials_dev, num, dd.data(),
                   generators ? raw_gens.p : nullptr, offset_generators, num_ranges, &wait_for_range,
@@ -452,106 +460,282 @@ private:
 };
 std::vector<std::unique_ptr<Worker>> g_workers;
 
+// Partial points of the k generator-range shards, gathered on the primary device (k x count points,
+// shard-major) and summed there. Direct device-to-device copies (NVLink when peer access exists;
+// cudaMemcpyPeerAsync stages through the host otherwise) — the only inter-GPU traffic of a call:
+// count x point_bytes per device (the reference stages the same partials through the
+// host, sxt/multiexp/pippenger2/multiexponentiation.h:105-137).
+struct Gather {
+  void* buf = nullptr;
+  size_t capacity = 0;
+  void* ensure(size_t bytes) {
+    if (bytes > capacity) {
+      if (buf) {
+        B200_CUDA(cudaStreamSynchronize(g_state.stream));
+        B200_CUDA(cudaFree(buf));
+      }
+      capacity = std::max<size_t>(bytes, 1u << 16);
+      B200_CUDA(cudaMalloc(&buf, capacity));
+    }
+    return buf;
+  }
+};
+Gather g_gather;
+
+// number of devices a generator range of n terms is split over
+size_t range_parts(uint64_t n) {
+  static const uint64_t min_terms = [] {
+    const char* env = std::getenv("BLITZAR_B200_MIN_SHARD_TERMS");  // test hook
+    return env ? std::strtoull(env, nullptr, 10) : (1ull << 15);
+  }();
+  return (size_t)std::max<uint64_t>(1, std::min<uint64_t>(g_workers.size() + 1, n / std::max<uint64_t>(min_terms, 1)));
+}
+State& state_of(size_t part) { return part == 0 ? g_state : g_workers[part - 1]->st; }
+// runs f(part) for part = 0 .. parts-1: part 0 on the calling thread, the others on their device's
+// worker thread; returns when all are done
+template <class F> void on_devices(size_t parts, F f) {
+  for (size_t p = 1; p < parts; ++p)
+    g_workers[p - 1]->submit([=] { f(p); });
+  f(0);
+  for (size_t p = 1; p < parts; ++p)
+    g_workers[p - 1]->wait();
+  B200_CUDA(cudaSetDevice(g_state.device));
+}
+// this shard's `count` partial points -> slot `part` of the primary device's gather buffer
+void send_partials(const State& st, size_t part, const void* partials_dev, size_t bytes,
+                   void* gather_base) {
+  unsigned char* dst = static_cast<unsigned char*>(gather_base) + part * bytes;
+  if (part == 0)
+    B200_CUDA(cudaMemcpyAsync(dst, partials_dev, bytes, cudaMemcpyDeviceToDevice, st.stream));
+  else
+    B200_CUDA(cudaMemcpyPeerAsync(dst, g_state.device, partials_dev, st.device, bytes, st.stream));
+  B200_CUDA(cudaStreamSynchronize(st.stream));
+}
+
 void commit_host(unsigned curve_id, void* commitments, uint32_t num,
                  const sxt_sequence_descriptor* d, const void* generators,
-                 uint64_t offset_generators, const char* fn) {
+                 uint64_t offset_generators, const char* fn, void* out_partials_dev = nullptr) {
   if (num == 0)
     return;
   std::lock_guard<std::mutex> lock(g_mutex);
   require_init(fn);
-  B200_REQUIRE(commitments != nullptr, "commitments == nullptr");
-  (void)longest_column(d, num);  // validates the descriptors before any thread starts
+  B200_REQUIRE(commitments != nullptr || out_partials_dev != nullptr, "commitments == nullptr");
+  const uint64_t n = longest_column(d, num);  // validates the descriptors before any thread starts
   if (curve_id != SXT_CURVE_RISTRETTO255)
     B200_REQUIRE(generators != nullptr, "generators == nullptr");
-  const size_t stride = vt(curve_id).abi_commit_bytes;
-  const size_t parts = std::min<size_t>(g_workers.size() + 1, num);
+  const CurveVTable& V = vt(curve_id);
+  const size_t stride = V.abi_commit_bytes;
+  const size_t devices = g_workers.size() + 1;
+  if (devices <= 1 || out_partials_dev) {
+    commit_on(g_state, curve_id, commitments, num, d, generators, offset_generators,
+              out_partials_dev);
+    return;
+  }
+  if (num >= devices) {
+    // ---- by column: contiguous column chunks balanced by scalar bytes, no exchange at all ---------
+    const size_t parts = devices;
+    std::vector<uint64_t> prefix(num + 1, 0);
+    for (uint32_t i = 0; i < num; ++i)
+      prefix[i + 1] = prefix[i] + d[i].n * d[i].element_nbytes + 1;
+    std::vector<uint32_t> cut(parts + 1, num);
+    cut[0] = 0;
+    for (size_t p = 1; p < parts; ++p) {
+      uint32_t c = cut[p - 1] + 1;
+      while (c < num - (parts - p) && prefix[c] * parts < prefix[num] * p)
+        ++c;
+      cut[p] = c;
+    }
+    on_devices(parts, [&, curve_id, commitments, d, generators, offset_generators](size_t p) {
+      commit_on(state_of(p), curve_id, static_cast<unsigned char*>(commitments) + cut[p] * stride,
+                cut[p + 1] - cut[p], d + cut[p], generators, offset_generators);
+    });
+    return;
+  }
+  // ---- by generator range (fewer columns than devices): device p computes the partial MSM of every
+  // column over rows [n p / k, n (p+1) / k); one partial point per column and device is gathered on
+  // the primary device and summed there (the MSM is linear)
+  const size_t parts = range_parts(n);
   if (parts <= 1) {
     commit_on(g_state, curve_id, commitments, num, d, generators, offset_generators);
     return;
   }
-  // contiguous column chunks balanced by scalar bytes; chunk 0 runs on the calling thread
-  std::vector<uint64_t> prefix(num + 1, 0);
-  for (uint32_t i = 0; i < num; ++i)
-    prefix[i + 1] = prefix[i] + d[i].n * d[i].element_nbytes + 1;
-  std::vector<uint32_t> cut(parts + 1, num);
-  cut[0] = 0;
-  for (size_t p = 1; p < parts; ++p) {
-    uint32_t c = cut[p - 1] + 1;
-    while (c < num - (parts - p) && prefix[c] * parts < prefix[num] * p)
-      ++c;
-    cut[p] = c;
-  }
-  for (size_t p = 1; p < parts; ++p) {
-    Worker* w = g_workers[p - 1].get();
-    const uint32_t b = cut[p], e = cut[p + 1];
-    w->submit([=] {
-      commit_on(w->st, curve_id, static_cast<unsigned char*>(commitments) + b * stride, e - b,
-                d + b, generators, offset_generators);
-    });
-  }
-  commit_on(g_state, curve_id, commitments, cut[1], d, generators, offset_generators);
-  for (size_t p = 1; p < parts; ++p)
-    g_workers[p - 1]->wait();
+  const size_t pbytes = (size_t)num * V.point_bytes;
+  void* gather = g_gather.ensure(parts * pbytes);
+  on_devices(parts, [&, curve_id, num, d, generators, offset_generators, n, parts, pbytes,
+                     gather](size_t p) {
+    State& st = state_of(p);
+    const uint64_t lo = n * p / parts, hi = n * (p + 1) / parts;
+    std::vector<sxt_sequence_descriptor> dd(d, d + num);
+    for (auto& c : dd) {
+      const uint64_t b = std::min<uint64_t>(lo, c.n), e = std::min<uint64_t>(hi, c.n);
+      c.data = c.data ? c.data + b * c.element_nbytes : nullptr;
+      c.n = e - b;
+    }
+    const unsigned char* g = static_cast<const unsigned char*>(generators);
+    DevBuf<unsigned char> part(pbytes, st.stream);
+    commit_on(st, curve_id, nullptr, num, dd.data(), g ? g + lo * V.abi_gen_bytes : nullptr,
+              offset_generators + lo, part.p);
+    send_partials(st, p, part.p, pbytes, gather);
+  });
+  cudaStream_t s = g_state.stream;
+  DevBuf<unsigned char> sum(pbytes, s);
+  DevBuf<unsigned char> out((size_t)num * stride, s);
+  V.sum_parts(ctx(), gather, (uint32_t)parts, num, sum.p);
+  V.store(ctx(), sum.p, out.p, num, true);
+  copy_d2h(commitments, out.p, (size_t)num * stride, s);
+  stream_sync(s);
 }
 
-// generators: n projective ABI structs (host memory, or device_resident: already in HBM), or —
-// compact_window != 0 — the table image of a reference partition-table file (host memory).
-// Builds the fixed-base table 2^(c w) G_i on the device (replaces the reference's CPU-serial
-// make_in_memory_partition_table_accessor, in_memory_partition_table_accessor_utility.h:41-79).
-Handle* handle_new(unsigned curve_id, const void* generators, unsigned n,
-                   bool device_resident = false, unsigned compact_window = 0,
-                   size_t compact_bytes = 0) {
+// sxt_multiexp_handle: one shard per device (BLITZAR_B200_DEVICES=k splits the generator range at
+// construction; SURVEY §8e "fixed-base handle: shard generators at sxt_multiexp_handle_new time")
+struct HandleSet {
+  unsigned curve_id = 0, n = 0;
+  std::vector<Handle*> shards;
+  std::vector<unsigned> first;  // first generator of every shard
+};
+
+// One shard on st's device (the calling thread's current device). generators: n projective ABI
+// structs (host memory, or device_resident: already in HBM), or — compact_window != 0 — the table
+// image of a reference partition-table file (host memory). Builds the fixed-base table 2^(c w) G_i
+// on the device (replaces the reference's CPU-serial make_in_memory_partition_table_accessor,
+// in_memory_partition_table_accessor_utility.h:41-79).
+Handle* shard_new(const State& st, unsigned curve_id, const void* generators, unsigned n,
+                  bool device_resident, unsigned compact_window, size_t compact_bytes) {
   const CurveVTable& V = vt(curve_id);
-  cudaStream_t s = g_state.stream;
+  cudaStream_t s = st.stream;
   Handle* h = new Handle{curve_id, n, nullptr};
   h->window_bits = choose_table_window(n, V.gen_bytes);
   h->windows = h->window_bits ? 256 / h->window_bits + 1 : 1;
   B200_CUDA(cudaMalloc(&h->gens, (size_t)(n ? n : 1) * h->windows * V.gen_bytes));
   if (n) {
     B200_REQUIRE(generators != nullptr, "generators == nullptr");
+    const EngineCtx cx = ctx_of(st);
     if (compact_window) {
       DevBuf<unsigned char> raw(compact_bytes, s);
       HostStager::get().copy(raw.p, generators, compact_bytes, s);
-      V.ingest_compact_table(ctx(), raw.p, compact_window, h->gens, n);
+      V.ingest_compact_table(cx, raw.p, compact_window, h->gens, n);
     } else if (device_resident) {
-      V.ingest_projective(ctx(), generators, h->gens, n);
+      V.ingest_projective(cx, generators, h->gens, n);
     } else {
       DevBuf<unsigned char> raw((size_t)n * V.abi_proj_bytes, s);
       HostStager::get().copy(raw.p, generators, (size_t)n * V.abi_proj_bytes, s);
-      V.ingest_projective(ctx(), raw.p, h->gens, n);
+      V.ingest_projective(cx, raw.p, h->gens, n);
     }
-    V.build_table(ctx(), h->gens, n, h->window_bits, h->windows);
+    V.build_table(cx, h->gens, n, h->window_bits, h->windows);
     stream_sync(s);
   }
   return h;
 }
 
-void fixed_host(void* res, const Handle* h, int mode, unsigned element_num_bytes,
+HandleSet* handle_new(unsigned curve_id, const void* generators, unsigned n,
+                      bool device_resident = false, unsigned compact_window = 0,
+                      size_t compact_bytes = 0) {
+  const CurveVTable& V = vt(curve_id);
+  HandleSet* hs = new HandleSet;
+  hs->curve_id = curve_id;
+  hs->n = n;
+  size_t parts = device_resident ? 1 : range_parts(n);
+  const unsigned align = compact_window ? compact_window : 1;  // shards start on a table group
+  hs->shards.assign(parts, nullptr);
+  hs->first.assign(parts + 1, n);
+  for (size_t p = 0; p < parts; ++p)
+    hs->first[p] = (unsigned)(((uint64_t)n * p / parts) / align * align);
+  on_devices(parts, [&, curve_id, generators, device_resident, compact_window](size_t p) {
+    const unsigned lo = hs->first[p], cnt = hs->first[p + 1] - lo;
+    const unsigned char* g = static_cast<const unsigned char*>(generators);
+    size_t off = 0, cbytes = 0;
+    if (compact_window) {
+      const size_t group_bytes = (size_t)V.abi_compact_bytes << compact_window;
+      off = (size_t)(lo / compact_window) * group_bytes;
+      cbytes = (size_t)((cnt + compact_window - 1) / compact_window) * group_bytes;
+    } else {
+      off = (size_t)lo * V.abi_proj_bytes;
+    }
+    hs->shards[p] = shard_new(state_of(p), curve_id, g ? g + off : nullptr, cnt, device_resident,
+                              compact_window, cbytes);
+  });
+  (void)compact_bytes;
+  return hs;
+}
+
+struct FixedCall {
+  int mode;
+  unsigned element_num_bytes;
+  const unsigned* bit_table;
+  const unsigned* lengths;
+  unsigned num_outputs, rows;
+  uint64_t row_bytes;
+};
+
+// rows [lo, lo + h->n) of a fixed-base call on st's device: canonical projective results to `res`
+// (host) or partial points to out_partials_dev
+void fixed_on(const State& st, void* res, const Handle* h, const FixedCall& c, unsigned lo,
+              const uint8_t* scalars, void* out_partials_dev) {
+  cudaStream_t s = st.stream;
+  const CurveVTable& V = vt(h->curve_id);
+  const unsigned hi = std::min<uint64_t>((uint64_t)lo + h->n, c.rows);
+  const unsigned rows = hi > lo ? hi - lo : 0;
+  std::vector<unsigned> lens;
+  if (c.mode == 2) {
+    lens.resize(c.num_outputs);
+    for (unsigned j = 0; j < c.num_outputs; ++j)
+      lens[j] = c.lengths[j] > lo ? std::min(c.lengths[j] - lo, rows) : 0u;
+  }
+  const size_t bytes = (size_t)c.row_bytes * rows;
+  DevBuf<unsigned char> scal(bytes + 64, s);
+  DevBuf<unsigned char> out((size_t)c.num_outputs * V.abi_proj_bytes, s);
+  HostStager::get().copy(scal.p, scalars + (size_t)c.row_bytes * lo, bytes, s);
+  V.fixed_device(ctx_of(st), out_partials_dev ? nullptr : out.p, out_partials_dev, h, c.mode,
+                 c.element_num_bytes, c.bit_table, c.mode == 2 ? lens.data() : nullptr,
+                 c.num_outputs, rows, scal.p);
+  if (!out_partials_dev)
+    copy_d2h(res, out.p, (size_t)c.num_outputs * V.abi_proj_bytes, s);
+  stream_sync(s);
+}
+
+void fixed_host(void* res, const HandleSet* hs, int mode, unsigned element_num_bytes,
                 const unsigned* bit_table, const unsigned* lengths, unsigned num_outputs,
                 unsigned n, const uint8_t* scalars, void* out_partials_dev = nullptr) {
   if (num_outputs == 0)
     return;
-  cudaStream_t s = g_state.stream;
+  FixedCall c{mode, element_num_bytes, bit_table, lengths, num_outputs, n, 0};
   uint64_t row_bits = 0;
-  unsigned rows = n;
   for (unsigned j = 0; j < num_outputs; ++j) {
     row_bits += mode == 0 ? 8ull * element_num_bytes : bit_table[j];
     if (mode == 2) {
       B200_REQUIRE(j == 0 || lengths[j] >= lengths[j - 1],
                    "output lengths must be sorted in ascending order");
-      rows = j == 0 ? lengths[j] : (lengths[j] > rows ? lengths[j] : rows);
+      c.rows = j == 0 ? lengths[j] : (lengths[j] > c.rows ? lengths[j] : c.rows);
     }
   }
-  size_t bytes = (size_t)((row_bits + 7) / 8) * rows;
-  B200_REQUIRE(bytes == 0 || scalars != nullptr, "scalars == nullptr");
-  DevBuf<unsigned char> scal(bytes + 64, s);
-  const CurveVTable& V = vt(h->curve_id);
+  c.row_bytes = (row_bits + 7) / 8;
+  B200_REQUIRE(c.rows <= hs->n, "more scalars than generators in the handle");
+  B200_REQUIRE(c.row_bytes * c.rows == 0 || scalars != nullptr, "scalars == nullptr");
+  const size_t parts = hs->shards.size();
+  if (parts == 1) {
+    fixed_on(g_state, res, hs->shards[0], c, 0, scalars, out_partials_dev);
+    return;
+  }
+  const CurveVTable& V = vt(hs->curve_id);
+  const size_t pbytes = (size_t)num_outputs * V.point_bytes;
+  void* gather = g_gather.ensure(parts * pbytes);
+  on_devices(parts, [&, hs, scalars, pbytes, gather](size_t p) {
+    State& st = state_of(p);
+    DevBuf<unsigned char> part(pbytes, st.stream);
+    fixed_on(st, nullptr, hs->shards[p], c, hs->first[p], scalars, part.p);
+    send_partials(st, p, part.p, pbytes, gather);
+  });
+  cudaStream_t s = g_state.stream;
+  if (out_partials_dev) {
+    V.sum_parts(ctx(), gather, (uint32_t)parts, num_outputs, out_partials_dev);
+    stream_sync(s);
+    return;
+  }
+  DevBuf<unsigned char> sum(pbytes, s);
   DevBuf<unsigned char> out((size_t)num_outputs * V.abi_proj_bytes, s);
-  HostStager::get().copy(scal.p, scalars, bytes, s);
-  V.fixed_device(ctx(), out_partials_dev ? nullptr : out.p, out_partials_dev, h, mode,
-                 element_num_bytes, bit_table, lengths, num_outputs, rows, scal.p);
-  if (!out_partials_dev)
-    copy_d2h(res, out.p, (size_t)num_outputs * V.abi_proj_bytes, s);
+  V.sum_parts(ctx(), gather, (uint32_t)parts, num_outputs, sum.p);
+  V.store(ctx(), sum.p, out.p, num_outputs, false);
+  copy_d2h(res, out.p, (size_t)num_outputs * V.abi_proj_bytes, s);
   stream_sync(s);
 }
 
@@ -754,11 +938,13 @@ void sxt_multiexp_handle_free(struct sxt_multiexp_handle* handle) {
   if (!handle)
     return;
   std::lock_guard<std::mutex> lock(g_mutex);
-  Handle* h = reinterpret_cast<Handle*>(handle);
-  B200_CUDA(cudaSetDevice(g_state.device));
-  B200_CUDA(cudaStreamSynchronize(g_state.stream));
-  B200_CUDA(cudaFree(h->gens));
-  delete h;
+  HandleSet* hs = reinterpret_cast<HandleSet*>(handle);
+  on_devices(hs->shards.size(), [hs](size_t p) {
+    B200_CUDA(cudaStreamSynchronize(state_of(p).stream));
+    B200_CUDA(cudaFree(hs->shards[p]->gens));
+    delete hs->shards[p];
+  });
+  delete hs;
 }
 
 // File format written (versioned): u32 magic "B2HD", u32 version = 1, u32 curve_id, u32 n, then n
@@ -769,16 +955,20 @@ void sxt_multiexp_handle_write_to_file(const struct sxt_multiexp_handle* handle,
                                        const char* filename) {
   std::lock_guard<std::mutex> lock(g_mutex);
   require_init("sxt_multiexp_handle_write_to_file");
-  const Handle* h = reinterpret_cast<const Handle*>(handle);
+  const HandleSet* h = reinterpret_cast<const HandleSet*>(handle);
   B200_REQUIRE(h && filename, "null handle or filename");
   const CurveVTable& V = vt(h->curve_id);
-  cudaStream_t s = g_state.stream;
   size_t bytes = (size_t)h->n * V.abi_proj_bytes;
-  DevBuf<unsigned char> out(bytes + 16, s);
-  V.gens_to_projective(ctx(), h->gens, out.p, h->n);
   std::vector<unsigned char> host(bytes);
-  copy_d2h(host.data(), out.p, bytes, s);
-  stream_sync(s);
+  on_devices(h->shards.size(), [&, h](size_t p) {
+    const State& st = state_of(p);
+    const Handle* sh = h->shards[p];
+    const size_t sb = (size_t)sh->n * V.abi_proj_bytes;
+    DevBuf<unsigned char> out(sb + 16, st.stream);
+    V.gens_to_projective(ctx_of(st), sh->gens, out.p, sh->n);
+    copy_d2h(host.data() + (size_t)h->first[p] * V.abi_proj_bytes, out.p, sb, st.stream);
+    stream_sync(st.stream);
+  });
   FILE* f = std::fopen(filename, "wb");
   B200_REQUIRE(f != nullptr, "cannot open handle file for writing");
   uint32_t hdr[4] = {kHandleMagic, 1u, h->curve_id, h->n};
@@ -832,7 +1022,7 @@ void sxt_fixed_multiexponentiation(void* res, const struct sxt_multiexp_handle* 
                                    const uint8_t* scalars) {
   std::lock_guard<std::mutex> lock(g_mutex);
   require_init("sxt_fixed_multiexponentiation");
-  const Handle* h = reinterpret_cast<const Handle*>(handle);
+  const HandleSet* h = reinterpret_cast<const HandleSet*>(handle);
   B200_REQUIRE(h != nullptr, "null handle");
   fixed_host(res, h, 0, element_num_bytes, nullptr, nullptr, num_outputs, n, scalars);
 }
@@ -841,7 +1031,7 @@ void sxt_fixed_packed_multiexponentiation(void* res, const struct sxt_multiexp_h
                                           unsigned n, const uint8_t* scalars) {
   std::lock_guard<std::mutex> lock(g_mutex);
   require_init("sxt_fixed_packed_multiexponentiation");
-  const Handle* h = reinterpret_cast<const Handle*>(handle);
+  const HandleSet* h = reinterpret_cast<const HandleSet*>(handle);
   B200_REQUIRE(h != nullptr, "null handle");
   fixed_host(res, h, 1, 0, output_bit_table, nullptr, num_outputs, n, scalars);
 }
@@ -851,7 +1041,7 @@ void sxt_fixed_vlen_multiexponentiation(void* res, const struct sxt_multiexp_han
                                         const uint8_t* scalars) {
   std::lock_guard<std::mutex> lock(g_mutex);
   require_init("sxt_fixed_vlen_multiexponentiation");
-  const Handle* h = reinterpret_cast<const Handle*>(handle);
+  const HandleSet* h = reinterpret_cast<const HandleSet*>(handle);
   B200_REQUIRE(h != nullptr, "null handle");
   fixed_host(res, h, 2, 0, output_bit_table, output_lengths, num_outputs, 0, scalars);
 }
@@ -950,7 +1140,7 @@ void b200_fixed_msm_host_partials(void* out_partials, const struct sxt_multiexp_
     return;
   std::lock_guard<std::mutex> lock(g_mutex);
   require_init("b200_fixed_msm_host_partials");
-  const Handle* h = reinterpret_cast<const Handle*>(handle);
+  const HandleSet* h = reinterpret_cast<const HandleSet*>(handle);
   B200_REQUIRE(h != nullptr && out_partials != nullptr, "null handle or out_partials");
   fixed_host(nullptr, h, mode, element_num_bytes, output_bit_table, output_lengths, num_outputs, n,
              scalars, out_partials);
@@ -990,8 +1180,10 @@ void b200_fixed_msm_device(void* out_res, void* out_partials,
     return;
   std::lock_guard<std::mutex> lock(g_mutex);
   require_init("b200_fixed_msm_device");
-  const Handle* h = reinterpret_cast<const Handle*>(handle);
-  B200_REQUIRE(h != nullptr, "null handle");
+  const HandleSet* hs = reinterpret_cast<const HandleSet*>(handle);
+  B200_REQUIRE(hs != nullptr, "null handle");
+  B200_REQUIRE(hs->shards.size() == 1, "device-resident fixed MSM needs a single-device handle");
+  const Handle* h = hs->shards[0];
   unsigned rows = n;
   if (mode == 2) {
     rows = 0;

@@ -1,0 +1,267 @@
+// Batch-affine bucket accumulation for the short Weierstrass curves (bls12-381 G1, bn254 G1,
+// Grumpkin): the first levels of the bucket sums are computed as AFFINE + AFFINE -> AFFINE additions
+// whose field inversions are shared by Montgomery's trick over the whole level, ~6 field
+// multiplications per addition against 11 multiplications + 2 multiplications by 3b of the complete
+// projective mixed addition (Renes-Costello-Batina Alg. 8) the chunk walk uses.
+//
+// Replaces, for these curves, the bulk of the work of mtxbk::bucket_accumulate
+// (sxt/multiexp/bucket_method/accumulation_kernel.h:38-75) / cg1o::add (sxt/curve_g1/operation/
+// add.cc:37-72) — 32 projective additions per term there.
+//
+// Layout: the counting sort pads every bucket to a multiple of 2^L slots (pad slots = identity), so
+// that level l+1 is simply out[j] = in[2j] + in[2j+1] with no compaction between levels: a pair never
+// straddles two buckets, the key of slot j at level l is the key of slot j << l at level 0. After L
+// levels (L from the mean bucket load: pads stay below a quarter of the slots) the surviving
+// ~2^-L fraction goes through the ordinary chunk walk + cascade.
+//
+// Every kernel is an index-parallel body (no shared memory): thread t owns B consecutive pairs,
+//   pass 1: den_i = x2 - x1 (2 y1 for a doubling, 1 when no addition is needed); prefix products are
+//           written to HBM, the thread's total to A[t];
+//   A is inverted in place by a 64-ary product tree (BatchUp / BatchTop / BatchDown bodies);
+//   pass 2: walks the pairs backwards, peeling one inverse per pair off A[t]^-1, and writes the sum.
+#pragma once
+#include "curve.cuh"
+#include "runtime.cuh"
+
+namespace b200 {
+
+constexpr u32 kPadIndex = 0x7fffffffu;  // generator index of a pad entry (identity)
+constexpr u32 kBatchGroup = 64;         // arity of the inversion tree
+constexpr u32 kBatchTop = 96;           // at most this many values are inverted by one serial thread
+
+// ---- in-place batch inversion of n non-zero field elements ----------------------------------------
+template <class F> struct BatchUpBody {
+  static constexpr int kBlock = 128;
+  const typename F::E* vals;
+  typename F::E* pre;
+  typename F::E* prod;
+  u64 n;
+  B200_HD void operator()(u64 j) const {
+    const u64 b = j * kBatchGroup, e = b + kBatchGroup < n ? b + kBatchGroup : n;
+    typename F::E acc = F::one();
+    for (u64 i = b; i < e; ++i) {
+      pre[i] = acc;
+      F::mul(acc, acc, vals[i]);
+    }
+    prod[j] = acc;
+  }
+};
+template <class F> struct BatchDownBody {
+  static constexpr int kBlock = 128;
+  typename F::E* vals;
+  const typename F::E* pre;
+  const typename F::E* prod;  // inverses of the group products
+  u64 n;
+  B200_HD void operator()(u64 j) const {
+    const u64 b = j * kBatchGroup, e = b + kBatchGroup < n ? b + kBatchGroup : n;
+    typename F::E inv = prod[j];
+    for (u64 i = e; i-- > b;) {
+      typename F::E t, v = vals[i];
+      F::mul(t, inv, pre[i]);
+      F::mul(inv, inv, v);
+      vals[i] = t;
+    }
+  }
+};
+template <class F> struct BatchTopBody {
+  static constexpr int kBlock = 32;
+  typename F::E* vals;
+  typename F::E* pre;
+  u64 n;
+  B200_HD void operator()(u64) const {
+    typename F::E acc = F::one(), inv;
+    for (u64 i = 0; i < n; ++i) {
+      pre[i] = acc;
+      F::mul(acc, acc, vals[i]);
+    }
+    F::invert(inv, acc);
+    for (u64 i = n; i-- > 0;) {
+      typename F::E t, v = vals[i];
+      F::mul(t, inv, pre[i]);
+      F::mul(inv, inv, v);
+      vals[i] = t;
+    }
+  }
+};
+template <class F> inline void batch_invert(stream_t s, typename F::E* vals, u64 n) {
+  typedef typename F::E E;
+  if (n == 0)
+    return;
+  E* pre = (E*)dev_alloc(n * sizeof(E), s);
+  if (n <= kBatchTop) {
+    launch(BatchTopBody<F>{vals, pre, n}, 1, s);
+  } else {
+    const u64 m = (n + kBatchGroup - 1) / kBatchGroup;
+    E* prod = (E*)dev_alloc(m * sizeof(E), s);
+    launch(BatchUpBody<F>{vals, pre, prod, n}, m, s);
+    batch_invert<F>(s, prod, m);
+    launch(BatchDownBody<F>{vals, pre, prod, n}, m, s);
+    dev_free(prod, s);
+  }
+  dev_free(pre, s);
+}
+
+// ---- one pair level --------------------------------------------------------------------------------
+template <class C> struct PairLevel {
+  typedef typename C::F F;
+  typedef typename F::E fe;
+  typedef typename C::Gen Gen;
+  // level 0 reads the sorted, padded entry list and gathers generators; later levels read the
+  // previous level's points
+  const u64* entries;
+  const Gen* gens;
+  const Gen* in;
+  const u32* m_ptr;  // number of padded level-0 slots (device)
+  u32 level;         // this level's inputs are slots of 2^level level-0 slots
+  u32 B;             // pairs per thread
+
+  B200_HD u64 valid_pairs() const { return (u64)(*m_ptr) >> (level + 1); }
+  B200_HD void load(Gen& a, u64 slot) const {
+    if (in) {
+      a = in[slot];
+      return;
+    }
+    const u64 ent = entries[slot];
+    const u32 idx = (u32)ent >> 1;
+    if (idx == kPadIndex) {
+      a.x = F::zero();
+      a.y = F::zero();
+      return;
+    }
+    a = gens[idx];
+    if (((u32)ent & 1u) && !C::gen_is_identity(a))
+      F::neg(a.y, a.y);
+  }
+  // 0 = chord addition, 1 = result is a, 2 = result is b, 3 = tangent (doubling), 4 = identity
+  B200_HD int classify(fe& den, const Gen& a, const Gen& b) const {
+    den = F::one();
+    if (C::gen_is_identity(b))
+      return 1;
+    if (C::gen_is_identity(a))
+      return 2;
+    if (F::equal(a.x, b.x)) {
+      fe s;
+      F::add(s, a.y, b.y);
+      if (F::is_zero(s))
+        return 4;
+      den = s;  // = 2 y
+      return 3;
+    }
+    F::sub(den, b.x, a.x);
+    return 0;
+  }
+};
+
+template <class C> struct PairPass1Body {
+  static constexpr int kBlock = 128;
+  typedef typename C::F F;
+  PairLevel<C> lv;
+  typename F::E* pre;     // one per pair
+  typename F::E* totals;  // one per thread
+  B200_HD void operator()(u64 t) const {
+    const u64 np = lv.valid_pairs();
+    const u64 b = t * lv.B, e = b + lv.B < np ? b + lv.B : np;
+    typename F::E acc = F::one();
+    for (u64 p = b; p < e; ++p) {
+      typename C::Gen x, y;
+      typename F::E den;
+      lv.load(x, 2 * p);
+      lv.load(y, 2 * p + 1);
+      lv.classify(den, x, y);
+      pre[p] = acc;
+      F::mul(acc, acc, den);
+    }
+    totals[t] = acc;
+  }
+};
+
+template <class C> struct PairPass2Body {
+  static constexpr int kBlock = 128;
+  typedef typename C::F F;
+  typedef typename F::E fe;
+  PairLevel<C> lv;
+  const fe* pre;
+  const fe* totals;  // inverted
+  typename C::Gen* out;
+  B200_HD void operator()(u64 t) const {
+    const u64 np = lv.valid_pairs();
+    const u64 b = t * lv.B, e = b + lv.B < np ? b + lv.B : np;
+    if (b >= e)
+      return;
+    fe inv_acc = totals[t];
+    for (u64 p = e; p-- > b;) {
+      typename C::Gen x, y, r;
+      fe den, inv;
+      lv.load(x, 2 * p);
+      lv.load(y, 2 * p + 1);
+      const int kind = lv.classify(den, x, y);
+      F::mul(inv, inv_acc, pre[p]);
+      F::mul(inv_acc, inv_acc, den);
+      if (kind == 1) {
+        r = x;
+      } else if (kind == 2) {
+        r = y;
+      } else if (kind == 4) {
+        r.x = F::zero();
+        r.y = F::zero();
+      } else {
+        fe num, lam, l2, dx;
+        if (kind == 3) {  // 3 x^2 / (2 y)
+          fe xx;
+          F::sqr(xx, x.x);
+          F::add(num, xx, xx);
+          F::add(num, num, xx);
+        } else {
+          F::sub(num, y.y, x.y);
+        }
+        F::mul(lam, num, inv);
+        F::sqr(l2, lam);
+        F::sub(l2, l2, x.x);
+        F::sub(r.x, l2, y.x);
+        F::sub(dx, x.x, r.x);
+        F::mul(l2, lam, dx);
+        F::sub(r.y, l2, x.y);
+      }
+      out[p] = r;
+    }
+  }
+};
+
+// counts -> counts rounded up to a multiple of 2^L (the scan of these gives the padded offsets)
+struct PadCountsBody {
+  static constexpr int kBlock = 256;
+  u32* counts;
+  u32 mask;  // 2^L - 1
+  B200_HD void operator()(u64 k) const { counts[k] = (counts[k] + mask) & ~mask; }
+};
+// pad entries behind the real entries of every bucket: [cursor[k], starts[k+1])
+struct FillPadsBody {
+  static constexpr int kBlock = 128;
+  const u32* starts;  // padded exclusive offsets, nkeys + 1
+  const u32* cursor;  // end of the real entries of every bucket (scatter cursor)
+  u64* entries;
+  B200_HD void operator()(u64 k) const {
+    const u64 pad = ((u64)k << 32) | ((u64)kPadIndex << 1);
+    for (u32 i = cursor[k]; i < starts[k + 1]; ++i)
+      entries[i] = pad;
+  }
+};
+// entry list of the level the chunk walk starts from: slot j holds the point of 2^L level-0 slots,
+// keyed like them
+struct FinalEntriesBody {
+  static constexpr int kBlock = 256;
+  const u64* entries0;
+  const u32* m_ptr;
+  u32 L;
+  u64* entries;
+  u32* m_out;
+  B200_HD void operator()(u64 j) const {
+    const u64 m = (u64)(*m_ptr) >> L;
+    if (j == 0)
+      *m_out = (u32)m;
+    if (j < m)
+      entries[j] = (entries0[j << L] & 0xffffffff00000000ull) | (j << 1);
+  }
+};
+
+}  // namespace b200

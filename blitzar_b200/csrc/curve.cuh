@@ -121,6 +121,7 @@ struct Ed25519 {
   static constexpr int kAbiProjBytes = 160;    // sxt_ristretto255 (handle generators, fixed res)
   static constexpr int kAbiCommitBytes = 32;   // sxt_ristretto255_compressed
   static constexpr int kScalarBitsHint = 253;
+  static constexpr bool kBatchAffine = false;  // extended coordinates: 8M per addition already
 
   struct Point {
     fe X, Y, Z, T;
@@ -541,6 +542,7 @@ template <class FieldT, class CP> struct Weierstrass {
   static constexpr int kAbiCommitBytes = CP::kAbiCommitBytes;
 
   static constexpr bool kFp64Accumulate = false;
+  static constexpr bool kBatchAffine = true;  // batch_affine.cuh
   struct Point {
     fe X, Y, Z;
   };

@@ -18,6 +18,8 @@ struct MsmOptions {
   u64 max_group_entries = 1ull << 30;  // columns are grouped below this many (term, window) entries
   u64 max_range_entries = 1ull << 31;  // one sort pass holds at most this many entries: longer
                                        // columns are processed as several generator ranges
+  int pair_levels = -1;  // batch-affine pair levels (Weierstrass): -1 = from the mean bucket load
+  u32 pair_batch = 0;    // pairs per thread of a pair level (0 = 32)
   u32 table_policy = 0;  // fixed-base tables: 0 = cost model decides, 1 = whenever available, 2 = never
 };
 

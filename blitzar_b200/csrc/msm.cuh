@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "batch_affine.cuh"
 #include "curve.cuh"
 #include "engine_api.cuh"
 
@@ -289,10 +290,11 @@ template <class C> struct FillIdentityBody {
 template <class C> struct MergeBucketsBody {
   static constexpr int kBlock = 128;
   const u32* bucket_end;
+  const u32* bucket_begin;  // padded layouts: start offset of every bucket; null = dense layout
   const typename C::Point* scratch;
   typename C::Point* buckets;
   B200_HD void operator()(u64 k) const {
-    const u32 lo = k ? bucket_end[k - 1] : 0u;
+    const u32 lo = bucket_begin ? bucket_begin[k] : (k ? bucket_end[k - 1] : 0u);
     if (bucket_end[k] == lo)
       return;
     typename C::Point b = buckets[k];
@@ -461,6 +463,21 @@ struct WindowUsedBody {
     u32 hi = bucket_end[(w + 1) * nbuckets - 1];
     if (hi != lo)
       window_used[w] = 1u;
+  }
+};
+
+// same flag from the per-bucket counts (before they are padded / scanned): thread t looks at 256 buckets
+struct WindowUsedFromCountsBody {
+  static constexpr int kBlock = 128;
+  const u32* counts;
+  u64 nkeys;
+  u32 nbuckets;
+  u32* window_used;
+  B200_HD void operator()(u64 t) const {
+    const u64 b = t * 256, e = b + 256 < nkeys ? b + 256 : nkeys;
+    for (u64 k = b; k < e; ++k)
+      if (counts[k])
+        window_used[k / nbuckets] = 1u;
   }
 };
 
@@ -759,32 +776,101 @@ void msm_accumulate_range(stream_t s, const MsmPlan& plan, const typename C::Gen
   const ColumnDesc* d_cols = (const ColumnDesc*)d_stage;
   const u64* d_col_start = (const u64*)(d_stage + desc_bytes);
 
+  StageRange nvtx_sort("msm: digit count + scan + scatter");
   u32* d_counts = (u32*)dev_alloc((nkeys + 1) * sizeof(u32), s);
   dev_zero(d_counts, (nkeys + 1) * sizeof(u32), s);
   launch(CountBody{d_cols, d_col_start, ncols, c, nbuckets, d_counts}, total_terms, s);
-  exclusive_scan(d_counts, nkeys + 1, s);  // d_counts[nkeys] = number of entries
+  // Batch-affine pair levels (short Weierstrass curves, large passes): L levels, buckets padded to
+  // multiples of 2^L slots; L from the mean bucket load so that pads stay below ~1/4 of the slots.
+  u32 L = 0;
+  if constexpr (C::kBatchAffine) {
+    const double mean = (double)max_entries / (double)nkeys;
+    if (opt.pair_levels >= 0)
+      L = (u32)opt.pair_levels;
+    else if (max_entries >= (1ull << 18))
+      while (L < 6 && (double)(4u << L) <= mean)
+        ++L;
+    while (L > 0 && max_entries + nkeys * ((1ull << L) - 1) >= (1ull << 32) - (1ull << L))
+      --L;
+  }
+  const u64 slots_max =
+      L ? ((max_entries + nkeys * ((1ull << L) - 1) + (1ull << L) - 1) >> L) << L : max_entries;
+  u32* d_starts = nullptr;
+  if (L) {
+    launch(WindowUsedFromCountsBody{d_counts, nkeys, nbuckets, d_window_used}, (nkeys + 255) / 256, s);
+    launch(PadCountsBody{d_counts, (1u << L) - 1u}, nkeys, s);
+  }
+  exclusive_scan(d_counts, nkeys + 1, s);  // d_counts[nkeys] = number of (padded) entries
   u32* d_m = (u32*)dev_alloc(16 * sizeof(u32), s);
   copy_d2d(d_m, d_counts + nkeys, sizeof(u32), s);
-  u64* d_entries = (u64*)dev_alloc(max_entries * sizeof(u64), s);
+  if (L) {
+    d_starts = (u32*)dev_alloc((nkeys + 1) * sizeof(u32), s);
+    copy_d2d(d_starts, d_counts, (nkeys + 1) * sizeof(u32), s);
+  }
+  u64* d_entries = (u64*)dev_alloc(slots_max * sizeof(u64), s);
   launch(ScatterBody{d_cols, d_col_start, ncols, c, nbuckets, d_counts, d_entries}, total_terms,
          s);
-  // d_counts[k] is now the END offset of bucket k
-  launch(WindowUsedBody{d_counts, nbuckets, d_window_used}, plan.total_windows, s);
+  // d_counts[k] is now the END offset of bucket k's real entries
+  if (L)
+    launch(FillPadsBody{d_starts, d_counts, d_entries}, nkeys, s);
+  else
+    launch(WindowUsedBody{d_counts, nbuckets, d_window_used}, plan.total_windows, s);
+
+  B200_LOG(3, "range [%llu, %llu): %llu terms, %llu entries max, c=%u, %llu keys, pair levels %u",
+           (unsigned long long)begin, (unsigned long long)end, (unsigned long long)total_terms,
+           (unsigned long long)max_entries, c, (unsigned long long)nkeys, L);
+  std::vector<void*> to_free;
+  const typename C::Gen* walk_gens = gens;
+  const u64* walk_entries = d_entries;
+  u64 m_max = max_entries;
+  u32* m_ptr = d_m;
+  KernelTimer::get().begin(s);
+  StageRange nvtx_acc("msm: bucket accumulation");
+  if constexpr (C::kBatchAffine) {
+    if (L) {
+      typedef typename C::F F;
+      typedef typename F::E fe;
+      typedef typename C::Gen Gen;
+      const u32 B = opt.pair_batch ? opt.pair_batch : 32u;
+      const Gen* in = nullptr;
+      for (u32 l = 0; l < L; ++l) {
+        const u64 npairs = slots_max >> (l + 1);
+        const u64 T = (npairs + B - 1) / B;
+        Gen* out = (Gen*)dev_alloc(npairs * sizeof(Gen), s);
+        fe* pre = (fe*)dev_alloc(npairs * sizeof(fe), s);
+        fe* totals = (fe*)dev_alloc(T * sizeof(fe), s);
+        PairLevel<C> lv{l == 0 ? d_entries : nullptr, l == 0 ? gens : nullptr, in, d_m, l, B};
+        launch(PairPass1Body<C>{lv, pre, totals}, T, s);
+        batch_invert<F>(s, totals, T);
+        launch(PairPass2Body<C>{lv, pre, totals, out}, T, s);
+        dev_free(pre, s);
+        dev_free(totals, s);
+        if (in)
+          dev_free((void*)in, s);
+        in = out;
+      }
+      m_max = slots_max >> L;
+      u64* entries_l = (u64*)dev_alloc(m_max * sizeof(u64), s);
+      launch(FinalEntriesBody{d_entries, d_m, L, entries_l, d_m + 9}, m_max, s);
+      to_free.push_back((void*)in);
+      to_free.push_back(entries_l);
+      walk_gens = in;
+      walk_entries = entries_l;
+      m_ptr = d_m + 9;
+    }
+  }
 
   // a chunk of K entries leaves 2 pieces, so K must exceed 2 for the cascade to shrink
   // measured on B200 (C2): K = 64 trims the cascade more than it costs the first level
-  const u32 chunk1_auto = max_entries >= (1ull << 23) ? 64u : 32u;
+  const u32 chunk1_auto = m_max >= (1ull << 23) ? 64u : 32u;
   const u32 chunk1 = opt.chunk1 == 0 ? chunk1_auto : (opt.chunk1 < 4 ? 4u : opt.chunk1);
   const u32 chunkn = opt.chunkn < 4 ? 4u : opt.chunkn;
   Point* d_target = d_buckets;
   if (add_into)  // later ranges: own bucket array, merged into the shared one below
     d_target = (Point*)dev_alloc(nkeys * sizeof(Point), s);
-  u64 m_max = max_entries;
   u32 K = chunk1;
   const u32* lvl_keys = nullptr;
   const Point* lvl_pieces = nullptr;
-  u32* m_ptr = d_m;
-  std::vector<void*> to_free;
   bool first = true;
   int level = 0;
   stream_t cs = s;  // stream of the current cascade level
@@ -802,9 +888,8 @@ void msm_accumulate_range(stream_t s, const MsmPlan& plan, const typename C::Gen
     }
     const u32 fin = final_level ? 1u : 0u;
     if (first) {
-      KernelTimer::get().begin(s);
-      launch(AccumulateBody<C, true>{nullptr, d_entries, gens, nullptr, m_ptr, K, fin, d_target,
-                                     out_keys, out_pieces, out_m},
+      launch(AccumulateBody<C, true>{nullptr, walk_entries, walk_gens, nullptr, m_ptr, K, fin,
+                                     d_target, out_keys, out_pieces, out_m},
              T, s);
       KernelTimer::get().end(s);
       if (tail != s) {
@@ -831,7 +916,7 @@ void msm_accumulate_range(stream_t s, const MsmPlan& plan, const typename C::Gen
     ++level;
   }
   if (add_into) {
-    launch(MergeBucketsBody<C>{d_counts, d_target, d_buckets}, nkeys, cs);
+    launch(MergeBucketsBody<C>{d_counts, d_starts, d_target, d_buckets}, nkeys, cs);
     dev_free(d_target, cs);
   }
   for (void* ptr : to_free)
@@ -839,6 +924,7 @@ void msm_accumulate_range(stream_t s, const MsmPlan& plan, const typename C::Gen
   dev_free(d_entries, s);
   dev_free(d_m, cs);
   dev_free(d_counts, cs);
+  dev_free(d_starts, cs);
   dev_free(d_stage, s);
 }
 
@@ -847,6 +933,7 @@ template <class C>
 void msm_finish(stream_t s, const MsmPlan& plan, const typename C::Point* d_buckets,
                 const u32* d_window_used, typename C::Point* out, const MsmOptions& opt) {
   typedef typename C::Point Point;
+  StageRange nvtx_fin("msm: bucket reduction + window combination");
   const u32 total_windows = plan.total_windows, nbuckets = plan.nbuckets, ncols = plan.ncols;
   ColumnDesc* d_cols =
       (ColumnDesc*)stage_to_device(s, plan.cols.data(), ncols * sizeof(ColumnDesc));
@@ -919,6 +1006,10 @@ void msm_run(stream_t s, const typename C::Gen* gens, std::vector<ColumnDesc> co
   if (cols.empty())
     return;
   MsmPlan plan = msm_make_plan(std::move(cols), opt, sizeof(Point));
+  B200_LOG(2, "msm: curve %u, %u columns, longest %llu, %llu terms, window %u bits, %u bucket sets%s",
+           C::kCurveId, plan.ncols, (unsigned long long)plan.max_n,
+           (unsigned long long)plan.total_terms, plan.c, plan.total_windows,
+           plan.ncols && plan.cols[0].table_n ? " (fixed-base table)" : "");
   if (plan.total_terms == 0 || plan.total_windows == 0) {
     if (hook)
       hook->before_range(0, plan.max_n);

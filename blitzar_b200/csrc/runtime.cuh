@@ -13,6 +13,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <cctype>
+#include <string>
 #include <utility>
 #include <vector>
 
@@ -20,6 +22,7 @@
 
 #ifndef B200_EMULATE
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #endif
 
 namespace b200 {
@@ -33,6 +36,49 @@ namespace b200 {
     if (!(cond))                                                                                   \
       ::b200::die(msg, __FILE__, __LINE__);                                                        \
   } while (0)
+
+// stderr log gated by BLITZAR_LOG_LEVEL (the reference's variable, sxt/base/log/setup.cc:28-55):
+// unset / error / critical / off -> silent; warn; info (one line per entry point: shapes, window
+// width, pieces, path taken); debug / trace (per stage).
+inline int log_level() {
+  static const int level = [] {
+    const char* env = std::getenv("BLITZAR_LOG_LEVEL");
+    if (!env)
+      return 0;
+    std::string s(env);
+    for (auto& ch : s)
+      ch = (char)std::tolower((unsigned char)ch);
+    if (s == "warn")
+      return 1;
+    if (s == "info")
+      return 2;
+    if (s == "debug" || s == "trace")
+      return 3;
+    return 0;
+  }();
+  return level;
+}
+#define B200_LOG(level, ...)                                                                       \
+  do {                                                                                             \
+    if (::b200::log_level() >= (level)) {                                                          \
+      std::fprintf(stderr, "[blitzar_b200] " __VA_ARGS__);                                         \
+      std::fputc('\n', stderr);                                                                    \
+    }                                                                                              \
+  } while (0)
+
+// NVTX range around a stage of the pipeline (visible in nsys / ncu --nvtx; free when no tool is
+// attached). The reference brackets its benchmark loop with cudaProfilerStart/Stop only
+// (benchmark/multi_commitment/benchmark.m.cc:205,221).
+struct StageRange {
+#ifndef B200_EMULATE
+  explicit StageRange(const char* name) { nvtxRangePushA(name); }
+  ~StageRange() { nvtxRangePop(); }
+#else
+  explicit StageRange(const char*) {}
+#endif
+  StageRange(const StageRange&) = delete;
+  StageRange& operator=(const StageRange&) = delete;
+};
 
 #ifndef B200_EMULATE
 #define B200_CUDA(call)                                                                            \

@@ -74,6 +74,11 @@ def set_builtin(num_precomputed=0, window_bits=0):
     lib().emul_set_builtin(C.c_uint64(num_precomputed), C.c_uint(window_bits))
 
 
+def set_pairs(levels=-1, batch=0):
+    """batch-affine pair levels of the Weierstrass accumulation (-1 = automatic)"""
+    lib().emul_set_pairs(C.c_int(levels), C.c_uint(batch))
+
+
 def set_ranges(num_ranges=1):
     lib().emul_set_ranges(C.c_uint(num_ranges))
 

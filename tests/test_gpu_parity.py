@@ -261,6 +261,46 @@ for curve, n, shapes in ((0, 5000, [(0, 32, 0), (-100, 16, 1), (0, 1, 0), (-4999
     assert common.same(curve, got, port.commit(curve, cols, gens)), curve
 cols = common.random_columns(rng, 3000, [(0, 8, 0)] * 9)  # built-in generators on every device
 assert np.array_equal(bb.compute_pedersen_commitments(0, cols, None, 11), port.commit(0, cols, None, 11))
+# fewer columns than devices: the generator RANGE is split, partial points gathered on device 0
+for curve, n, shapes in ((0, 5003, [(0, 32, 0)]), (1, 1300, [(0, 32, 0), (-700, 16, 1)]),
+                         (2, 2100, [(-1, 32, 0)]), (3, 999, [(0, 8, 1)])):
+    gens, _ = common.generators_for(port, curve, n)
+    cols = common.random_columns(rng, n, shapes)
+    got = bb.compute_pedersen_commitments(curve, cols, gens)
+    assert common.same(curve, got, port.commit(curve, cols, gens)), ("range", curve)
+cols = common.random_columns(rng, 4000, [(0, 32, 0)])
+assert np.array_equal(bb.compute_pedersen_commitments(0, cols, None, 5), port.commit(0, cols, None, 5))
+# handles are sharded over the devices at construction; fixed / packed / vlen calls and the file
+import tempfile, os
+for curve in range(4):
+    m = 1100
+    _, gens_p = common.generators_for(port, curve, m)
+    h = bb.MultiexpHandle(curve, gens_p)
+    sc = rng.integers(0, 256, (m, 2 * 32), dtype=np.uint8)
+    a = h.fixed_multiexponentiation(32, 2, m, sc)
+    b = port.fixed_msm(curve, gens_p, 2, m, sc, element_num_bytes=32)
+    assert common.same(curve, port.normalize(curve, a), port.normalize(curve, b)), ("fixed", curve)
+    a = h.fixed_multiexponentiation(32, 2, 300, sc[:300])  # fewer rows than generators
+    b = port.fixed_msm(curve, gens_p, 2, 300, sc[:300], element_num_bytes=32)
+    assert common.same(curve, port.normalize(curve, a), port.normalize(curve, b)), ("fixed300", curve)
+    bt = [3, 1, 14, 64, 5, 200]
+    psc = rng.integers(0, 256, (m, (sum(bt) + 7) // 8), dtype=np.uint8)
+    lens = [1, 2, 17, 400, 900, m]
+    a = h.fixed_vlen_multiexponentiation(bt, lens, psc)
+    b = port.fixed_msm(curve, gens_p, len(bt), m, psc, output_bit_table=bt, output_lengths=lens)
+    assert common.same(curve, port.normalize(curve, a), port.normalize(curve, b)), ("vlen", curve)
+    path = os.path.join(tempfile.mkdtemp(), "h.bin")
+    h.write_to_file(path)
+    h2 = bb.MultiexpHandle(curve, filename=path)
+    a2 = h2.fixed_vlen_multiexponentiation(bt, lens, psc)
+    assert common.same(curve, port.normalize(curve, a2), port.normalize(curve, b)), ("file", curve)
+    h.free(); h2.free()
+    h3 = bb.MultiexpHandle(curve, filename=os.path.join(sys.argv[1], "tests", "golden", f"ref_table_curve{curve}_w3.bin"))
+    g7 = np.load(os.path.join(sys.argv[1], "tests", "golden", f"fixed_curve{curve}.npz"))["generators_p"][:7]
+    s7 = rng.integers(0, 256, (7, 32), dtype=np.uint8)
+    assert common.same(curve, port.normalize(curve, h3.fixed_multiexponentiation(32, 1, 7, s7)),
+                       port.normalize(curve, port.fixed_msm(curve, g7, 1, 7, s7, element_num_bytes=32)))
+    h3.free()
 print("multi-device ok")
 """
 
@@ -274,7 +314,8 @@ def test_columns_split_over_devices(bb):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, BLITZAR_B200_DEVICES=str(min(4, torch.cuda.device_count())))
+    env = dict(os.environ, BLITZAR_B200_DEVICES=str(min(4, torch.cuda.device_count())),
+               BLITZAR_B200_MIN_SHARD_TERMS="200")
     r = subprocess.run([sys.executable, "-c", _MULTI_DEVICE_SCRIPT, root], env=env, cwd=root,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "multi-device ok" in r.stdout, r.stdout + r.stderr
