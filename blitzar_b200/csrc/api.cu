@@ -192,7 +192,14 @@ public:
 
 private:
   static constexpr size_t kChunk = 8u << 20;
-  static constexpr int kSlots = 4, kWorkers = 4;
+  static constexpr int kSlots = 4;
+  // threads copying one chunk into the pinned ring (the caller's included); a B200 host has on the
+  // order of 100 cores and one core moves ~10 GB/s, PCIe 5 x16 wants ~55 GB/s
+  const int kWorkers = [] {
+    const char* env = std::getenv("BLITZAR_B200_STAGER_THREADS");
+    const int v = env ? std::atoi(env) : 8;
+    return std::max(1, std::min(32, v));
+  }();
   unsigned char* staging_[kSlots] = {};
   cudaEvent_t done_[kSlots] = {};
   unsigned next_ = 0;
@@ -263,6 +270,12 @@ private:
     cv_work_.notify_all();
     for (auto& t : workers_)
       t.join();
+    for (int i = 0; i < kSlots; ++i) {  // errors ignored: the context may already be gone at exit
+      if (staging_[i])
+        cudaFreeHost(staging_[i]);
+      if (done_[i])
+        cudaEventDestroy(done_[i]);
+    }
   }
 };
 

@@ -26,8 +26,9 @@
 namespace b200 {
 
 constexpr u32 kPadIndex = 0x7fffffffu;  // generator index of a pad entry (identity)
-constexpr u32 kBatchGroup = 64;         // arity of the inversion tree
-constexpr u32 kBatchTop = 96;           // at most this many values are inverted by one serial thread
+constexpr u32 kBatchGroup = 8;          // arity of the inversion tree: short serial chains per thread, the
+                                        // levels above the first are latency-bound either way
+constexpr u32 kBatchTop = 64;           // at most this many values reach the top of the tree
 
 // ---- in-place batch inversion of n non-zero field elements ----------------------------------------
 template <class F> struct BatchUpBody {
@@ -63,41 +64,32 @@ template <class F> struct BatchDownBody {
     }
   }
 };
+// top of the tree: at most kBatchTop values, one Fermat inversion per thread (all in parallel: the
+// latency of ONE inversion, without a serial prefix / back-substitution pass around it)
 template <class F> struct BatchTopBody {
   static constexpr int kBlock = 32;
   typename F::E* vals;
-  typename F::E* pre;
-  u64 n;
-  B200_HD void operator()(u64) const {
-    typename F::E acc = F::one(), inv;
-    for (u64 i = 0; i < n; ++i) {
-      pre[i] = acc;
-      F::mul(acc, acc, vals[i]);
-    }
-    F::invert(inv, acc);
-    for (u64 i = n; i-- > 0;) {
-      typename F::E t, v = vals[i];
-      F::mul(t, inv, pre[i]);
-      F::mul(inv, inv, v);
-      vals[i] = t;
-    }
+  B200_HD void operator()(u64 i) const {
+    typename F::E inv;
+    F::invert(inv, vals[i]);
+    vals[i] = inv;
   }
 };
 template <class F> inline void batch_invert(stream_t s, typename F::E* vals, u64 n) {
   typedef typename F::E E;
   if (n == 0)
     return;
-  E* pre = (E*)dev_alloc(n * sizeof(E), s);
   if (n <= kBatchTop) {
-    launch(BatchTopBody<F>{vals, pre, n}, 1, s);
-  } else {
-    const u64 m = (n + kBatchGroup - 1) / kBatchGroup;
-    E* prod = (E*)dev_alloc(m * sizeof(E), s);
-    launch(BatchUpBody<F>{vals, pre, prod, n}, m, s);
-    batch_invert<F>(s, prod, m);
-    launch(BatchDownBody<F>{vals, pre, prod, n}, m, s);
-    dev_free(prod, s);
+    launch(BatchTopBody<F>{vals}, n, s);
+    return;
   }
+  E* pre = (E*)dev_alloc(n * sizeof(E), s);
+  const u64 m = (n + kBatchGroup - 1) / kBatchGroup;
+  E* prod = (E*)dev_alloc(m * sizeof(E), s);
+  launch(BatchUpBody<F>{vals, pre, prod, n}, m, s);
+  batch_invert<F>(s, prod, m);
+  launch(BatchDownBody<F>{vals, pre, prod, n}, m, s);
+  dev_free(prod, s);
   dev_free(pre, s);
 }
 
@@ -152,22 +144,37 @@ template <class C> struct PairLevel {
   }
 };
 
+// Pass 1 of level 0 (later levels get theirs fused into the previous level's pass 2): only the x
+// coordinates are gathered — half the bytes of this HBM-bound pass — and y is fetched for the rare
+// pairs that need it (equal x, or x = 0 where (0,0) encodes the identity).
 template <class C> struct PairPass1Body {
   static constexpr int kBlock = 128;
   typedef typename C::F F;
+  typedef typename F::E fe;
   PairLevel<C> lv;
-  typename F::E* pre;     // one per pair
-  typename F::E* totals;  // one per thread
+  fe* pre;     // one per pair
+  fe* totals;  // one per thread
+  u64 t0;      // first thread of this launch (the level is launched in two halves on two streams)
   B200_HD void operator()(u64 t) const {
+    t += t0;
     const u64 np = lv.valid_pairs();
     const u64 b = t * lv.B, e = b + lv.B < np ? b + lv.B : np;
-    typename F::E acc = F::one();
+    fe acc = F::one();
     for (u64 p = b; p < e; ++p) {
-      typename C::Gen x, y;
-      typename F::E den;
-      lv.load(x, 2 * p);
-      lv.load(y, 2 * p + 1);
-      lv.classify(den, x, y);
+      const u64 ea = lv.entries[2 * p], eb = lv.entries[2 * p + 1];
+      const u32 ia = (u32)ea >> 1, ib = (u32)eb >> 1;
+      fe den = F::one();
+      if (ia != kPadIndex && ib != kPadIndex) {
+        const fe xa = lv.gens[ia].x, xb = lv.gens[ib].x;
+        if (F::equal(xa, xb) || F::is_zero(xa) || F::is_zero(xb)) {
+          typename C::Gen ga, gb;  // rare: the full classification
+          lv.load(ga, 2 * p);
+          lv.load(gb, 2 * p + 1);
+          lv.classify(den, ga, gb);
+        } else {
+          F::sub(den, xb, xa);
+        }
+      }
       pre[p] = acc;
       F::mul(acc, acc, den);
     }
@@ -175,55 +182,106 @@ template <class C> struct PairPass1Body {
   }
 };
 
+// Pass 2 of level l, fused with pass 1 of level l+1: the sums a thread writes are exactly the inputs
+// of its own pairs one level up (B halves per level), so their denominators and prefix products are
+// formed on the spot — one heavy kernel per level and no second read of the points. The prefix of
+// level l+1 is therefore built in the order level l is walked, and each level is walked against the
+// order its own prefix was built in: `descending` alternates from level to level.
 template <class C> struct PairPass2Body {
   static constexpr int kBlock = 128;
+  static constexpr int kMinBlocks = C::F::N > 8 ? 2 : 3;  // 168-register cap for the 8-limb fields
   typedef typename C::F F;
   typedef typename F::E fe;
+  typedef typename C::Gen Gen;
   PairLevel<C> lv;
   const fe* pre;
   const fe* totals;  // inverted
-  typename C::Gen* out;
+  Gen* out;
+  fe* pre_next;     // null on the last level
+  fe* totals_next;
+  u32 descending;
+  u64 t0;
+  B200_HD void add_pair(Gen& r, const Gen& x, const Gen& y, int kind, const fe& inv) const {
+    if (kind == 1) {
+      r = x;
+    } else if (kind == 2) {
+      r = y;
+    } else if (kind == 4) {
+      r.x = F::zero();
+      r.y = F::zero();
+    } else {
+      fe num, lam, l2, dx;
+      if (kind == 3) {  // 3 x^2 / (2 y)
+        fe xx;
+        F::sqr(xx, x.x);
+        F::add(num, xx, xx);
+        F::add(num, num, xx);
+      } else {
+        F::sub(num, y.y, x.y);
+      }
+      F::mul(lam, num, inv);
+      F::sqr(l2, lam);
+      F::sub(l2, l2, x.x);
+      F::sub(r.x, l2, y.x);
+      F::sub(dx, x.x, r.x);
+      F::mul(l2, lam, dx);
+      F::sub(r.y, l2, x.y);
+    }
+  }
   B200_HD void operator()(u64 t) const {
+    t += t0;
     const u64 np = lv.valid_pairs();
     const u64 b = t * lv.B, e = b + lv.B < np ? b + lv.B : np;
-    if (b >= e)
+    if (b >= e) {
+      if (pre_next)
+        totals_next[t] = F::one();  // the inversion tree multiplies every thread's total
       return;
-    fe inv_acc = totals[t];
-    for (u64 p = e; p-- > b;) {
-      typename C::Gen x, y, r;
-      fe den, inv;
-      lv.load(x, 2 * p);
-      lv.load(y, 2 * p + 1);
-      const int kind = lv.classify(den, x, y);
-      F::mul(inv, inv_acc, pre[p]);
-      F::mul(inv_acc, inv_acc, den);
-      if (kind == 1) {
-        r = x;
-      } else if (kind == 2) {
-        r = y;
-      } else if (kind == 4) {
-        r.x = F::zero();
-        r.y = F::zero();
-      } else {
-        fe num, lam, l2, dx;
-        if (kind == 3) {  // 3 x^2 / (2 y)
-          fe xx;
-          F::sqr(xx, x.x);
-          F::add(num, xx, xx);
-          F::add(num, num, xx);
-        } else {
-          F::sub(num, y.y, x.y);
-        }
-        F::mul(lam, num, inv);
-        F::sqr(l2, lam);
-        F::sub(l2, l2, x.x);
-        F::sub(r.x, l2, y.x);
-        F::sub(dx, x.x, r.x);
-        F::mul(l2, lam, dx);
-        F::sub(r.y, l2, x.y);
-      }
-      out[p] = r;
     }
+    const u64 cnt = e - b;
+    fe inv_acc = totals[t], acc_next = F::one();
+    Gen held;
+    // operands of the next pair are loaded before the current addition is computed
+    u64 p = descending ? e - 1 : b;
+    Gen xn, yn;
+    fe pn;
+    lv.load(xn, 2 * p);
+    lv.load(yn, 2 * p + 1);
+    pn = pre[p];
+    for (u64 k = 0; k < cnt; ++k) {
+      const Gen x = xn, y = yn;
+      const fe pr = pn;
+      const u64 cur = p;
+      if (k + 1 < cnt) {
+        p = descending ? p - 1 : p + 1;
+        lv.load(xn, 2 * p);
+        lv.load(yn, 2 * p + 1);
+        pn = pre[p];
+      }
+      fe den, inv;
+      Gen r;
+      const int kind = lv.classify(den, x, y);
+      F::mul(inv, inv_acc, pr);
+      F::mul(inv_acc, inv_acc, den);
+      add_pair(r, x, y, kind, inv);
+      out[cur] = r;
+      if (pre_next) {
+        // the element reached first is the odd one when walking down, the even one when walking up
+        const bool second = descending ? (cur & 1u) == 0 : (cur & 1u) != 0;
+        if (!second) {
+          held = r;
+        } else {
+          fe den2;
+          if (descending)
+            lv.classify(den2, r, held);
+          else
+            lv.classify(den2, held, r);
+          pre_next[cur >> 1] = acc_next;
+          F::mul(acc_next, acc_next, den2);
+        }
+      }
+    }
+    if (pre_next)
+      totals_next[t] = acc_next;
   }
 };
 

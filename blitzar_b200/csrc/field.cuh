@@ -853,6 +853,18 @@ struct BlsParams {
   static B200_HD u32 gx(int i) { return BLS_GX(i); }
   static B200_HD u32 gy(int i) { return BLS_GY(i); }
 };
+// scalars modulo the ristretto255 group order l (inner-product argument; replaces the device half of
+// sxt/scalar25/operation/{mul,muladd,add}.cc)
+struct Sc25Params {
+  static constexpr int N = 8;
+  static constexpr u32 inv = SC25_INV;
+  static B200_HD u32 p(int i) { return SC25_P(i); }
+  static B200_HD u32 one(int i) { return SC25_ONE(i); }
+  static B200_HD u32 r2(int i) { return SC25_R2(i); }
+  static B200_HD u32 pm2(int i) { return SC25_PM2(i); }
+  static B200_HD u32 half(int i) { return SC25_HALF(i); }
+};
+typedef Mont<Sc25Params> FSc25;
 typedef Mont<BnParams> FBn;
 typedef Mont<GkParams> FGk;
 typedef Mont<BlsParams> FBls;

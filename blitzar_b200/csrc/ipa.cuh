@@ -64,6 +64,88 @@ struct DecodeToGenBody {
   }
 };
 
+// ---- scalar work of the prover on the device (FSc25: Montgomery arithmetic mod l on 8 x u32 limbs;
+// a 32-byte little-endian scalar IS an FSc25 element in plain form). Replaces the reference's
+// scalar_fold_kernel / inner-product kernels (sxt/proof/inner_product/gpu_driver.cc:104-221,
+// sxt/scalar25/operation/inner_product.cc). mul(x R, y) = x y keeps vectors in plain form.
+typedef FSc25 FS;
+typedef FS::E ScE;
+B200_HD ScE sc_r2() {
+  ScE r;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    r.l[i] = Sc25Params::r2(i);
+  return r;
+}
+// any 256-bit value -> canonical residue (s25o::reduce32)
+struct IpaReduceBody {
+  static constexpr int kBlock = 128;
+  ScE* v;
+  B200_HD void operator()(u64 i) const {
+    ScE t;
+    FS::mul(t, v[i], sc_r2());
+    FS::from_mont(v[i], t);
+  }
+};
+// per-thread partial sums of <a_lo, b_hi> and <a_hi, b_lo> (each product carries a factor R^-1)
+struct IpaDotBody {
+  static constexpr int kBlock = 64;
+  const ScE* a;
+  const ScE* b;
+  u64 mid, nl, nr;  // products in the left / right sum
+  u32 K;
+  ScE* partial;  // 2 per thread
+  B200_HD void operator()(u64 t) const {
+    ScE cl = FS::zero(), cr = FS::zero(), p;
+    const u64 b0 = t * K, e0 = b0 + K;
+    for (u64 i = b0; i < e0; ++i) {
+      if (i < nl) {
+        FS::mul(p, a[i], b[mid + i]);
+        FS::add(cl, cl, p);
+      }
+      if (i < nr) {
+        FS::mul(p, a[mid + i], b[i]);
+        FS::add(cr, cr, p);
+      }
+    }
+    partial[2 * t] = cl;
+    partial[2 * t + 1] = cr;
+  }
+};
+// sums the partials (thread 0: left, thread 1: right), removes the R^-1 and writes the scalar of Q
+struct IpaDotFinalBody {
+  static constexpr int kBlock = 32;
+  const ScE* partial;
+  u64 T;
+  ScE* out_l;
+  ScE* out_r;
+  B200_HD void operator()(u64 side) const {
+    ScE acc = FS::zero();
+    for (u64 t = 0; t < T; ++t)
+      FS::add(acc, acc, partial[2 * t + side]);
+    FS::mul(acc, acc, sc_r2());
+    *(side ? out_r : out_l) = acc;
+  }
+};
+// out[i] = m_lo * v[i] + m_hi * v[mid + i] (v zero-padded to 2 mid; prfip::fold_scalars); the
+// multipliers are in Montgomery form
+struct IpaFoldScalarsBody {
+  static constexpr int kBlock = 128;
+  const ScE* v;
+  u64 mid, hi;  // hi = number of elements in the upper half
+  ScE m_lo, m_hi;
+  ScE* out;
+  B200_HD void operator()(u64 i) const {
+    ScE t, u;
+    FS::mul(t, m_lo, v[i]);
+    if (i < hi) {
+      FS::mul(u, m_hi, v[mid + i]);
+      FS::add(t, t, u);
+    }
+    out[i] = t;
+  }
+};
+
 struct Ipa {
   typedef Ed25519 C;
   typedef CurveOps<C> Ops;
@@ -119,6 +201,40 @@ struct Ipa {
     copy_d2h(out32, enc.p, 32, s);
     stream_sync(s);
   }
+  // sum_i s_i * gens[i] + extra_scalar * extra_gen with every input in HBM; the 32-byte encoding is
+  // left in out32_dev (no synchronisation)
+  static void msm_compressed_device(const EngineCtx& ctx, unsigned char* out32_dev,
+                                    const C::Gen* gens, uint64_t n, const ScE* scalars,
+                                    const C::Gen* extra_gen, const ScE* extra_scalar) {
+    stream_t s = ctx.s;
+    const uint64_t total = n + 1;
+    DevBuf<C::Gen> tg(total, s);
+    DevBuf<ScE> ts(total + 1, s);
+    copy_d2d(tg.p, gens, n * sizeof(C::Gen), s);
+    copy_d2d(ts.p, scalars, n * sizeof(ScE), s);
+    copy_d2d(tg.p + n, extra_gen, sizeof(C::Gen), s);
+    copy_d2d(ts.p + n, extra_scalar, sizeof(ScE), s);
+    std::vector<ColumnDesc> cols(1);
+    cols[0].base = (const unsigned char*)ts.p;
+    cols[0].row_stride = 32;
+    cols[0].bit_offset = 0;
+    cols[0].bit_width = 256;
+    cols[0].n = (u32)total;
+    cols[0].is_signed = 0;
+    cols[0].first_window = cols[0].num_windows = 0;
+    DevBuf<C::Point> pt(1, s);
+    Ops::run_columns(ctx, tg.p, cols, pt.p);
+    launch(StoreBody<C, true>{pt.p, out32_dev}, 1, s);
+  }
+  static ScE to_device_mont(const Sc& x) {  // x R mod l as device limbs
+    const Sc m = sc_to_mont(x);
+    ScE r;
+    for (int i = 0; i < 4; ++i) {
+      r.l[2 * i] = (u32)m.v[i];
+      r.l[2 * i + 1] = (u32)(m.v[i] >> 32);
+    }
+    return r;
+  }
   // m_lo * v[i] + m_hi * v[mid + i], with v zero-padded to 2 * mid (prfip::fold_scalars)
   static std::vector<uint8_t> fold_scalars(const std::vector<uint8_t>& v, const Sc& m_lo,
                                            const Sc& m_hi, uint64_t mid) {
@@ -159,38 +275,63 @@ struct Ipa {
     DevBuf<C::Gen> gstore(np + 1, s);
     const C::Gen* G0 = generators(ctx, gstore, generators_offset, np + 1);
     const C::Gen* Q = G0 + np;
-    DevBuf<C::Gen> gwork(np / 2, s);
+    DevBuf<C::Gen> gwork(np / 2, s), gwork2(np / 4 + 1, s);
     const C::Gen* G = G0;
-    std::vector<uint8_t> a(a_vector, a_vector + 32 * n), b(b_vector, b_vector + 32 * n);
-    uint64_t len = np;
+    // a, b live in HBM for the whole proof (ping-pong halves); the host sees only L, R (64 bytes) and
+    // the challenge of every round — one stream synchronisation per round, for the transcript
+    DevBuf<ScE> abuf(np + np / 2 + 2, s), bbuf(np + np / 2 + 2, s);
+    ScE* a = abuf.p;
+    ScE* b = bbuf.p;
+    ScE* a_next = abuf.p + np;
+    ScE* b_next = bbuf.p + np;
+    copy_h2d(a, a_vector, 32 * n, s);
+    copy_h2d(b, b_vector, 32 * n, s);
+    launch(IpaReduceBody{a}, n, s);
+    launch(IpaReduceBody{b}, n, s);
+    const u32 K = 64;
+    DevBuf<ScE> partial(2 * ((np / 2 + K - 1) / K) + 2, s), cq(2, s);
+    DevBuf<unsigned char> lr(64, s);
+    uint64_t len = np, na = n, nb = n;
     for (unsigned round = 0; round < k; ++round) {
       const uint64_t mid = len / 2;
-      const uint64_t na = a.size() / 32, nb = b.size() / 32;
       const uint64_t a_hi = na - mid, b_hi = nb - mid;
-      Sc c_l = sc_inner_product(&a[0], &b[32 * mid], std::min<uint64_t>(mid, b_hi));
-      Sc c_r = sc_inner_product(&a[32 * mid], &b[0], std::min<uint64_t>(a_hi, mid));
+      const uint64_t nl = std::min<uint64_t>(mid, b_hi), nr = std::min<uint64_t>(a_hi, mid);
+      const uint64_t T = (mid + K - 1) / K;
+      launch(IpaDotBody{a, b, mid, nl, nr, K, partial.p}, T, s);
+      launch(IpaDotFinalBody{partial.p, T, cq.p, cq.p + 1}, 2, s);
       uint8_t* l_out = l_vector + 32 * round;
       uint8_t* r_out = r_vector + 32 * round;
-      msm_compressed(ctx, l_out, G + mid, mid, &a[0], Q, &c_l);
-      msm_compressed(ctx, r_out, G, a_hi, &a[32 * mid], Q, &c_r);
+      msm_compressed_device(ctx, lr.p, G + mid, mid, a, Q, cq.p);
+      msm_compressed_device(ctx, lr.p + 32, G, a_hi, a + mid, Q, cq.p + 1);
+      uint8_t lr_host[64];
+      copy_d2h(lr_host, lr.p, 64, s);
+      stream_sync(s);
+      std::memcpy(l_out, lr_host, 32);
+      std::memcpy(r_out, lr_host + 32, 32);
       Sc x = round_challenge(tr, l_out, r_out);
       Sc x_inv = sc_inv(x);
-      a = fold_scalars(a, x, x_inv, mid);
+      const ScE xm = to_device_mont(x), xim = to_device_mont(x_inv);
+      launch(IpaFoldScalarsBody{a, mid, a_hi, xm, xim, a_next}, mid, s);
+      std::swap(a, a_next);
+      na = mid;
       if (mid == 1)
         break;
-      b = fold_scalars(b, x_inv, x, mid);
+      launch(IpaFoldScalarsBody{b, mid, b_hi, xim, xm, b_next}, mid, s);
+      std::swap(b, b_next);
+      nb = mid;
       FoldGeneratorsBody body;
       body.g = G;
       body.mid = (u32)mid;
       scalar_words(body.m_lo, x_inv);
       scalar_words(body.m_hi, x);
-      body.out = gwork.p;
+      C::Gen* gout = (G == gwork.p) ? gwork2.p : gwork.p;
+      body.out = gout;
       launch(body, mid, s);
-      G = gwork.p;
+      G = gout;
       len = mid;
     }
+    copy_d2h(ap_value, a, 32, s);
     stream_sync(s);
-    std::memcpy(ap_value, &a[0], 32);
   }
 
   static int verify(const EngineCtx& ctx, uint8_t* transcript203, uint64_t n,

@@ -788,8 +788,8 @@ void msm_accumulate_range(stream_t s, const MsmPlan& plan, const typename C::Gen
     if (opt.pair_levels >= 0)
       L = (u32)opt.pair_levels;
     else if (max_entries >= (1ull << 18))
-      while (L < 6 && (double)(4u << L) <= mean)
-        ++L;
+      while (L < 6 && (double)(32u << L) <= mean)  // measured on B200: 2 levels at a mean load of 64,
+        ++L;                                        // 3 at 128 (tests/pair_timing.py)
     while (L > 0 && max_entries + nkeys * ((1ull << L) - 1) >= (1ull << 32) - (1ull << L))
       --L;
   }
@@ -831,24 +831,59 @@ void msm_accumulate_range(stream_t s, const MsmPlan& plan, const typename C::Gen
       typedef typename C::F F;
       typedef typename F::E fe;
       typedef typename C::Gen Gen;
-      const u32 B = opt.pair_batch ? opt.pair_batch : 32u;
+      // pairs per thread halve from level to level (a thread's sums are its own next-level inputs)
+      u32 B = opt.pair_batch ? opt.pair_batch : 32u;
+      while (B < (1u << L))
+        B *= 2;
+      B = (B >> (L - 1)) << (L - 1);
+      const u64 T = ((slots_max >> 1) + B - 1) / B;  // the same threads at every level
+      // The level is cut in two halves of threads (A, B) on two streams. The heavy passes are chained
+      // A, B, A, B, ... by events, so the inversion tree of one half (a chain of small latency-bound
+      // kernels ending in one Fermat inversion) runs under the heavy pass of the other half instead
+      // of leaving the GPU idle once per level. A thread's next-level inputs are its own outputs, so
+      // the halves never read each other's data.
+      stream_t s2 = aux_stream();
+      const u64 Ta = T / 2, Tb = T - Ta;
       const Gen* in = nullptr;
+      fe* pre = (fe*)dev_alloc((slots_max >> 1) * sizeof(fe), s);
+      fe* totals = (fe*)dev_alloc(T * sizeof(fe), s);
+      std::vector<void*> level_bufs = {pre, totals};
+      {
+        PairLevel<C> lv0{d_entries, gens, nullptr, d_m, 0, B};
+        launch(PairPass1Body<C>{lv0, pre, totals, 0}, Ta, s);
+        stream_follow(s2, s);
+        launch(PairPass1Body<C>{lv0, pre, totals, Ta}, Tb, s2);
+      }
       for (u32 l = 0; l < L; ++l) {
         const u64 npairs = slots_max >> (l + 1);
-        const u64 T = (npairs + B - 1) / B;
+        const bool last = l + 1 == L;
+        // buffers of the next level come from the main stream's pool; the second stream touches
+        // them only after following the main stream past this point
         Gen* out = (Gen*)dev_alloc(npairs * sizeof(Gen), s);
-        fe* pre = (fe*)dev_alloc(npairs * sizeof(fe), s);
-        fe* totals = (fe*)dev_alloc(T * sizeof(fe), s);
-        PairLevel<C> lv{l == 0 ? d_entries : nullptr, l == 0 ? gens : nullptr, in, d_m, l, B};
-        launch(PairPass1Body<C>{lv, pre, totals}, T, s);
-        batch_invert<F>(s, totals, T);
-        launch(PairPass2Body<C>{lv, pre, totals, out}, T, s);
-        dev_free(pre, s);
-        dev_free(totals, s);
-        if (in)
-          dev_free((void*)in, s);
+        fe* pre_next = last ? nullptr : (fe*)dev_alloc((npairs >> 1) * sizeof(fe), s);
+        fe* totals_next = last ? nullptr : (fe*)dev_alloc(T * sizeof(fe), s);
+        level_bufs.push_back(out);
+        if (!last) {
+          level_bufs.push_back(pre_next);
+          level_bufs.push_back(totals_next);
+        }
+        PairLevel<C> lv{l == 0 ? d_entries : nullptr, l == 0 ? gens : nullptr, in, d_m, l, B >> l};
+        const u32 desc = (l & 1u) ? 0u : 1u;
+        batch_invert<F>(s, totals, Ta);
+        stream_follow(s, s2);  // after the other half's previous heavy pass
+        launch(PairPass2Body<C>{lv, pre, totals, out, pre_next, totals_next, desc, 0}, Ta, s);
+        batch_invert<F>(s2, totals + Ta, Tb);
+        stream_follow(s2, s);
+        launch(PairPass2Body<C>{lv, pre, totals, out, pre_next, totals_next, desc, Ta}, Tb, s2);
         in = out;
+        pre = pre_next;
+        totals = totals_next;
       }
+      stream_follow(s, s2);
+      level_bufs.pop_back();  // the last level's points feed the chunk walk (freed with to_free)
+      for (void* ptr : level_bufs)
+        if (ptr != (void*)in)
+          dev_free(ptr, s);
       m_max = slots_max >> L;
       u64* entries_l = (u64*)dev_alloc(m_max * sizeof(u64), s);
       launch(FinalEntriesBody{d_entries, d_m, L, entries_l, d_m + 9}, m_max, s);

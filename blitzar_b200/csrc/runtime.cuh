@@ -154,6 +154,14 @@ inline void stream_follow(stream_t later, stream_t earlier) {
   B200_CUDA(cudaStreamWaitEvent(later, e, 0));
 }
 
+// a second stream of the calling thread (= of its device), for stages whose halves can overlap
+inline stream_t aux_stream() {
+  static thread_local cudaStream_t s = nullptr;
+  if (!s)
+    B200_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  return s;
+}
+
 // Small host->device parameter blocks (column descriptors, prefix tables). A pageable
 // cudaMemcpyAsync synchronises the stream, which would stall the launch queue once per range; the
 // blocks therefore go through a ring of pinned slots and are copied truly asynchronously. A slot is
@@ -264,6 +272,7 @@ inline void copy_d2h(void* h, const void* d, size_t bytes, stream_t) { std::memc
 inline void copy_d2d(void* d, const void* s_, size_t bytes, stream_t) { std::memcpy(d, s_, bytes); }
 inline void stream_sync(stream_t) {}
 inline void stream_follow(stream_t, stream_t) {}
+inline stream_t aux_stream() { return 0; }
 inline void* stage_to_device(stream_t s, const void* host, size_t bytes) {
   void* d = dev_alloc(bytes, s);
   std::memcpy(d, host, bytes);
