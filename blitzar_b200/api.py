@@ -38,6 +38,7 @@ B200_SYMBOLS = [
     "b200_profile_read", "b200_set_reduce_groups", "b200_stream",
     "b200_synthetic_generators_device", "b200_commit_host_partials",
     "b200_fixed_msm_host_partials", "b200_multiexp_handle_new_device",
+    "b200_selftest_lane_arithmetic",
 ]
 
 
@@ -261,6 +262,11 @@ def commit_device(curve_id, columns_shape, scalar_ptrs, generators_ptr, out_comm
     lib().b200_commit_device(C.c_uint(curve_id), C.c_void_p(out_commit_ptr),
                              C.c_void_p(out_partial_ptr), C.c_uint32(num), arr,
                              C.c_void_p(generators_ptr), C.c_uint64(offset_generators))
+
+
+def selftest_lane_arithmetic(warps=64, seed=1):
+    lib().b200_selftest_lane_arithmetic.restype = C.c_uint
+    return int(lib().b200_selftest_lane_arithmetic(C.c_uint(warps), C.c_uint(seed)))
 
 
 def synthetic_generators_device(curve_id, out_ptr, n, first=0, projective=False):

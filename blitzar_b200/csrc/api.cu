@@ -52,6 +52,10 @@ EngineCtx ctx_of(const State& st) {
     c.tail = st.tail_stream;
   if (const char* env = std::getenv("BLITZAR_B200_GROUP_ENTRIES"))  // test hook: force column groups
     c.opt.max_group_entries = std::strtoull(env, nullptr, 10);
+  if (const char* env = std::getenv("BLITZAR_B200_LANE_TAIL"))
+    c.opt.lane_tail = (u32)std::atoi(env);
+  if (const char* env = std::getenv("BLITZAR_B200_SCATTER_WM"))
+    c.opt.scatter_window_major = (u32)std::atoi(env);
   if (const char* env = std::getenv("BLITZAR_B200_PAIR_LEVELS"))  // batch-affine levels (-1 = auto)
     c.opt.pair_levels = std::atoi(env);
   if (const char* env = std::getenv("BLITZAR_B200_PAIR_BATCH"))
@@ -1214,6 +1218,11 @@ void b200_synthetic_generators_device(unsigned curve_id, void* out_generators, u
   require_init("b200_synthetic_generators_device");
   B200_REQUIRE(out_generators != nullptr, "out_generators == nullptr");
   vt(curve_id).synth_generators(ctx(), out_generators, n, first, projective != 0);
+}
+unsigned b200_selftest_lane_arithmetic(unsigned warps, unsigned seed) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  require_init("b200_selftest_lane_arithmetic");
+  return selftest_lane_arithmetic(ctx(), warps, seed);
 }
 void b200_set_reduce_groups(unsigned g1, unsigned gn) {
   std::lock_guard<std::mutex> lock(g_mutex);

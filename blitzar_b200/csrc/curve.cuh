@@ -360,7 +360,10 @@ struct Ed25519 {
 
   // x = sqrt(u/v) helper of RFC 9496 §4.2 (SQRT_RATIO_M1); same contract as
   // rstb::compute_sqrt_ratio_m1 (sxt/ristretto/base/sqrt_ratio_m1.cc:33-67).
-  static B200_HD int sqrt_ratio_m1(fe& x, const fe& u, const fe& v) {
+  struct ScalarPow {  // the per-thread chain; LanePow (lanefield.cuh) spreads it over 8 lanes
+    static B200_HD void pow22523(fe& r, const fe& a) { F::pow22523(r, a); }
+  };
+  template <class Pow = ScalarPow> static B200_HD int sqrt_ratio_m1(fe& x, const fe& u, const fe& v) {
     fe v3, vxx, t, chk;
     const fe sqrtm1 = F::constant([](int i) { return F25_SQRTM1(i); });
     F::sqr(v3, v);
@@ -368,7 +371,7 @@ struct Ed25519 {
     F::sqr(x, v3);
     F::mul(x, x, u);
     F::mul(x, x, v);  // u v^7
-    F::pow22523(x, x);
+    Pow::pow22523(x, x);
     F::mul(x, x, v3);
     F::mul(x, x, u);  // u v^3 (u v^7)^((p-5)/8)
     F::sqr(vxx, x);
@@ -390,6 +393,9 @@ struct Ed25519 {
   // ristretto255 encoding (RFC 9496 §4.3.2); same result as rstb::to_bytes
   // (sxt/ristretto/base/byte_conversion.cc:74-129).
   static B200_HD void store_commit_abi(void* dst, const Point& p) {
+    encode<ScalarPow>((unsigned char*)dst, p);
+  }
+  template <class Pow> static B200_HD void encode(unsigned char* dst, const Point& p) {
     fe u1, u2, zmy, u1u2u2, inv_sqrt, den1, den2, z_inv, ix, iy, eden, t_z_inv, x_, y_, den_inv,
         x_z_inv, s_, ny;
     const fe one = F::one();
@@ -400,7 +406,7 @@ struct Ed25519 {
     F::mul(u2, p.X, p.Y);
     F::sqr(u1u2u2, u2);
     F::mul(u1u2u2, u1, u1u2u2);
-    (void)sqrt_ratio_m1(inv_sqrt, one, u1u2u2);
+    (void)sqrt_ratio_m1<Pow>(inv_sqrt, one, u1u2u2);
     F::mul(den1, inv_sqrt, u1);
     F::mul(den2, inv_sqrt, u2);
     F::mul(z_inv, den1, den2);
@@ -419,7 +425,7 @@ struct Ed25519 {
     F::sub(s_, p.Z, y_);
     F::mul(s_, den_inv, s_);
     F::abs(s_, s_);
-    F::to_bytes((unsigned char*)dst, s_);
+    F::to_bytes(dst, s_);
   }
 
   // ristretto255 decoding (RFC 9496 §4.3.1); same contract as rstb::from_bytes

@@ -7,6 +7,22 @@ B200_DEFINE_CURVE_VTABLE(kVTableEd25519, Ed25519);
 void launch_builtin_generators(const EngineCtx& ctx, void* gens, uint64_t first, uint64_t n) {
   launch(BuiltinGeneratorBody{(Ed25519::Gen*)gens, first}, n, ctx.s);
 }
+unsigned selftest_lane_arithmetic(const EngineCtx& ctx, unsigned warps, unsigned seed) {
+#ifdef B200_LANE_TAIL
+  DevBuf<u32> bad(1, ctx.s);
+  dev_zero(bad.p, sizeof(u32), ctx.s);
+  launch(lane8::SelfTestBody{seed, bad.p}, (u64)warps * 32, ctx.s);
+  u32 host = 0;
+  copy_d2h(&host, bad.p, sizeof(u32), ctx.s);
+  stream_sync(ctx.s);
+  return host;
+#else
+  (void)ctx;
+  (void)warps;
+  (void)seed;
+  return 0;
+#endif
+}
 void ipa_prove(const EngineCtx& ctx, uint8_t* l_vector, uint8_t* r_vector, uint8_t* ap_value,
                uint8_t* transcript203, uint64_t n, uint64_t generators_offset,
                const uint8_t* a_vector, const uint8_t* b_vector) {

@@ -146,7 +146,7 @@ template <class C> struct CurveOps {
     }
     run_columns(rctx, gens_ptr, cols, pts, num_ranges ? num_ranges : 1, &hook);
     if (out_commitments)
-      launch(StoreBody<C, true>{pts, (unsigned char*)out_commitments}, num, s);
+      launch_store_commit<C>(s, pts, (unsigned char*)out_commitments, num, ctx.opt.lane_tail != 0);
   }
 
   // fixed-base MSM over a handle's device-resident generators (mode 0 fixed width, 1 packed, 2 vlen)
@@ -211,7 +211,8 @@ template <class C> struct CurveOps {
   static void store(const EngineCtx& ctx, const void* pts, void* out_dev, uint64_t count,
                     bool commit) {
     if (commit)
-      launch(StoreBody<C, true>{(const Point*)pts, (unsigned char*)out_dev}, count, ctx.s);
+      launch_store_commit<C>(ctx.s, (const Point*)pts, (unsigned char*)out_dev, count,
+                             ctx.opt.lane_tail != 0);
     else
       launch(StoreBody<C, false>{(const Point*)pts, (unsigned char*)out_dev}, count, ctx.s);
   }

@@ -20,6 +20,8 @@ struct MsmOptions {
                                        // columns are processed as several generator ranges
   int pair_levels = -1;  // batch-affine pair levels (Weierstrass): -1 = from the mean bucket load
   u32 pair_batch = 0;    // pairs per thread of a pair level (0 = 32)
+  u32 lane_tail = 1;  // warp-cooperative (lane-sliced) Horner / encoding kernels for ed25519
+  u32 scatter_window_major = 0;  // scatter with one thread per (window, term), window-major
   u32 table_policy = 0;  // fixed-base tables: 0 = cost model decides, 1 = whenever available, 2 = never
 };
 
@@ -119,6 +121,10 @@ int ipa_verify(const EngineCtx& ctx, uint8_t* transcript203, uint64_t n,
                uint64_t generators_offset, const uint8_t* b_vector, const uint8_t* product,
                const uint8_t* a_commit160, const uint8_t* l_vector, const uint8_t* r_vector,
                const uint8_t* ap_value);
+
+// lane-sliced field arithmetic self-test (lanefield.cuh): number of mismatching checks over
+// `warps` warps of pseudo-random / edge-case operands
+unsigned selftest_lane_arithmetic(const EngineCtx& ctx, unsigned warps, unsigned seed);
 
 // built-in ristretto generators g(first .. first+n) into the device generator layout
 void launch_builtin_generators(const EngineCtx& ctx, void* gens, uint64_t first, uint64_t n);

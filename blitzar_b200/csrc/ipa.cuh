@@ -146,6 +146,31 @@ struct IpaFoldScalarsBody {
   }
 };
 
+// The two MSMs of a round as TWO COLUMNS of one engine call over the generator array
+// [G_lo | G_hi | Q] (len + 1 entries): column L = [0 .. 0 | a_lo | c_L], column R = [a_hi, 0 .. | 0 .. 0
+// | c_R]. Zero scalars produce no bucket entries, and the latency-bound tail of a small MSM (bucket
+// reduction, 240 Horner doublings, ristretto encoding) is paid once per round instead of twice.
+struct IpaRoundColumnsBody {
+  static constexpr int kBlock = 128;
+  const ScE* a;
+  const ScE* cq;  // c_L, c_R
+  u64 mid, a_hi;
+  ScE* col_l;  // 2 mid + 1 entries each
+  ScE* col_r;
+  B200_HD void operator()(u64 i) const {
+    const ScE zero = FS::zero();
+    if (i < mid) {
+      col_l[i] = zero;
+      col_l[mid + i] = a[i];
+      col_r[i] = i < a_hi ? a[mid + i] : zero;
+      col_r[mid + i] = zero;
+    } else {
+      col_l[2 * mid] = cq[0];
+      col_r[2 * mid] = cq[1];
+    }
+  }
+};
+
 struct Ipa {
   typedef Ed25519 C;
   typedef CurveOps<C> Ops;
@@ -197,34 +222,27 @@ struct Ipa {
     DevBuf<C::Point> pt(1, s);
     DevBuf<unsigned char> enc(32, s);
     Ops::run_columns(ctx, tg.p, cols, pt.p);
-    launch(StoreBody<C, true>{pt.p, enc.p}, 1, s);
+    launch_store_commit<C>(s, pt.p, enc.p, 1, ctx.opt.lane_tail != 0);
     copy_d2h(out32, enc.p, 32, s);
     stream_sync(s);
   }
-  // sum_i s_i * gens[i] + extra_scalar * extra_gen with every input in HBM; the 32-byte encoding is
-  // left in out32_dev (no synchronisation)
-  static void msm_compressed_device(const EngineCtx& ctx, unsigned char* out32_dev,
-                                    const C::Gen* gens, uint64_t n, const ScE* scalars,
-                                    const C::Gen* extra_gen, const ScE* extra_scalar) {
+  // both points of a round: out64_dev = [L | R] encodings; gens = [G (len) | Q]
+  static void round_msms_device(const EngineCtx& ctx, unsigned char* out64_dev, const C::Gen* gens_q,
+                                uint64_t len, const ScE* col_l, const ScE* col_r) {
     stream_t s = ctx.s;
-    const uint64_t total = n + 1;
-    DevBuf<C::Gen> tg(total, s);
-    DevBuf<ScE> ts(total + 1, s);
-    copy_d2d(tg.p, gens, n * sizeof(C::Gen), s);
-    copy_d2d(ts.p, scalars, n * sizeof(ScE), s);
-    copy_d2d(tg.p + n, extra_gen, sizeof(C::Gen), s);
-    copy_d2d(ts.p + n, extra_scalar, sizeof(ScE), s);
-    std::vector<ColumnDesc> cols(1);
-    cols[0].base = (const unsigned char*)ts.p;
-    cols[0].row_stride = 32;
-    cols[0].bit_offset = 0;
-    cols[0].bit_width = 256;
-    cols[0].n = (u32)total;
-    cols[0].is_signed = 0;
-    cols[0].first_window = cols[0].num_windows = 0;
-    DevBuf<C::Point> pt(1, s);
-    Ops::run_columns(ctx, tg.p, cols, pt.p);
-    launch(StoreBody<C, true>{pt.p, out32_dev}, 1, s);
+    std::vector<ColumnDesc> cols(2);
+    for (int j = 0; j < 2; ++j) {
+      cols[j].base = (const unsigned char*)(j ? col_r : col_l);
+      cols[j].row_stride = 32;
+      cols[j].bit_offset = 0;
+      cols[j].bit_width = 256;
+      cols[j].n = (u32)(len + 1);
+      cols[j].is_signed = 0;
+      cols[j].first_window = cols[j].num_windows = 0;
+    }
+    DevBuf<C::Point> pt(2, s);
+    Ops::run_columns(ctx, gens_q, cols, pt.p);
+    launch_store_commit<C>(s, pt.p, out64_dev, 2, ctx.opt.lane_tail != 0);
   }
   static ScE to_device_mont(const Sc& x) {  // x R mod l as device limbs
     const Sc m = sc_to_mont(x);
@@ -232,20 +250,6 @@ struct Ipa {
     for (int i = 0; i < 4; ++i) {
       r.l[2 * i] = (u32)m.v[i];
       r.l[2 * i + 1] = (u32)(m.v[i] >> 32);
-    }
-    return r;
-  }
-  // m_lo * v[i] + m_hi * v[mid + i], with v zero-padded to 2 * mid (prfip::fold_scalars)
-  static std::vector<uint8_t> fold_scalars(const std::vector<uint8_t>& v, const Sc& m_lo,
-                                           const Sc& m_hi, uint64_t mid) {
-    const uint64_t len = v.size() / 32, p = len - mid;
-    std::vector<uint8_t> r(32 * mid);
-    const Sc lo_m = sc_to_mont(m_lo), hi_m = sc_to_mont(m_hi);  // one Montgomery product per term
-    for (uint64_t i = 0; i < mid; ++i) {
-      Sc t = sc_mul_mont(lo_m, sc_load(&v[32 * i]));
-      if (i < p)
-        t = sc_add(t, sc_mul_mont(hi_m, sc_load(&v[32 * (mid + i)])));
-      sc_store(&r[32 * i], t);
     }
     return r;
   }
@@ -275,8 +279,9 @@ struct Ipa {
     DevBuf<C::Gen> gstore(np + 1, s);
     const C::Gen* G0 = generators(ctx, gstore, generators_offset, np + 1);
     const C::Gen* Q = G0 + np;
-    DevBuf<C::Gen> gwork(np / 2, s), gwork2(np / 4 + 1, s);
-    const C::Gen* G = G0;
+    // folded generators: every buffer keeps Q in the slot after its last generator
+    DevBuf<C::Gen> gwork(np / 2 + 1, s), gwork2(np / 4 + 2, s);
+    const C::Gen* G = G0;  // G0[np] is Q already
     // a, b live in HBM for the whole proof (ping-pong halves); the host sees only L, R (64 bytes) and
     // the challenge of every round — one stream synchronisation per round, for the transcript
     DevBuf<ScE> abuf(np + np / 2 + 2, s), bbuf(np + np / 2 + 2, s);
@@ -289,7 +294,8 @@ struct Ipa {
     launch(IpaReduceBody{a}, n, s);
     launch(IpaReduceBody{b}, n, s);
     const u32 K = 64;
-    DevBuf<ScE> partial(2 * ((np / 2 + K - 1) / K) + 2, s), cq(2, s);
+    DevBuf<ScE> partial(2 * ((np / 2 + K - 1) / K) + 2, s), cq(2, s), col_l(np + 1, s),
+        col_r(np + 1, s);
     DevBuf<unsigned char> lr(64, s);
     uint64_t len = np, na = n, nb = n;
     for (unsigned round = 0; round < k; ++round) {
@@ -301,8 +307,8 @@ struct Ipa {
       launch(IpaDotFinalBody{partial.p, T, cq.p, cq.p + 1}, 2, s);
       uint8_t* l_out = l_vector + 32 * round;
       uint8_t* r_out = r_vector + 32 * round;
-      msm_compressed_device(ctx, lr.p, G + mid, mid, a, Q, cq.p);
-      msm_compressed_device(ctx, lr.p + 32, G, a_hi, a + mid, Q, cq.p + 1);
+      launch(IpaRoundColumnsBody{a, cq.p, mid, a_hi, col_l.p, col_r.p}, mid + 1, s);
+      round_msms_device(ctx, lr.p, G, len, col_l.p, col_r.p);
       uint8_t lr_host[64];
       copy_d2h(lr_host, lr.p, 64, s);
       stream_sync(s);
@@ -327,6 +333,7 @@ struct Ipa {
       C::Gen* gout = (G == gwork.p) ? gwork2.p : gwork.p;
       body.out = gout;
       launch(body, mid, s);
+      copy_d2d(gout + mid, Q, sizeof(C::Gen), s);
       G = gout;
       len = mid;
     }

@@ -23,6 +23,7 @@
 #include "batch_affine.cuh"
 #include "curve.cuh"
 #include "engine_api.cuh"
+#include "lanefield.cuh"
 
 namespace b200 {
 
@@ -120,14 +121,19 @@ B200_HD void load_scalar_bits(u32 v[8], bool& negative, const ColumnDesc& col, u
 }
 
 // Signed c-bit digit recoding; calls f(key, negate, window) for every non-zero digit.
+// only_window != kAllWindows: only that window's digit is reported (the recoding still walks the
+// windows below it for the carry).
+constexpr u32 kAllWindows = 0xffffffffu;
 template <class Fn>
 B200_HD void for_each_digit(const u32 v[8], bool negative, const ColumnDesc& col, u32 c,
-                            u32 nbuckets, Fn f) {
+                            u32 nbuckets, Fn f, u32 only_window = kAllWindows) {
   const u32 half = nbuckets;  // 2^(c-1)
   const u32 mask = (1u << c) - 1u;
   u64 buf = 0;
   u32 nb = 0, w = 0, carry = 0;
-  const u32 W = col.num_windows;
+  const u32 W = only_window == kAllWindows
+                    ? col.num_windows
+                    : (only_window < col.num_windows ? only_window + 1 : 0u);
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     buf |= (u64)v[k] << nb;
@@ -140,7 +146,7 @@ B200_HD void for_each_digit(const u32 v[8], bool negative, const ColumnDesc& col
       carry = dneg ? 1u : 0u;
       if (dneg)
         d = (1u << c) - d;
-      if (d)
+      if (d && (only_window == kAllWindows || w == only_window))
         f((col.first_window + (col.table_n ? 0u : w)) * nbuckets + (d - 1u), negative != dneg, w);
       ++w;
     }
@@ -152,7 +158,7 @@ B200_HD void for_each_digit(const u32 v[8], bool negative, const ColumnDesc& col
     carry = dneg ? 1u : 0u;
     if (dneg)
       d = (1u << c) - d;
-    if (d)
+    if (d && (only_window == kAllWindows || w == only_window))
       f((col.first_window + (col.table_n ? 0u : w)) * nbuckets + (d - 1u), negative != dneg, w);
     ++w;
   }
@@ -197,9 +203,20 @@ struct ScatterBody {
   u32 ncols, c, nbuckets;
   u32* cursor;  // exclusive offsets, consumed
   u64* entries;  // (key << 32) | (generator index << 1) | negate
+  // window-major order (total_terms != 0): thread = (window, term), all threads of one window run
+  // together, so the 8-byte scatter writes of a launch wave land in ONE window's slice of the entry
+  // array (n x 8 B) and merge in L2 before they reach HBM, instead of spreading over all windows
+  u64 total_terms;
   B200_HD void operator()(u64 tid) const {
+    u32 only = kAllWindows;
+    if (total_terms) {
+      only = (u32)(tid / total_terms);
+      tid -= (u64)only * total_terms;
+    }
     const u32 j = column_of(col_start, ncols, tid);
     const ColumnDesc col = cols[j];
+    if (only != kAllWindows && only >= col.num_windows)
+      return;
     u64 i = tid - col_start[j];
     u32 v[8];
     bool neg;
@@ -210,7 +227,7 @@ struct ScatterBody {
     for_each_digit(v, neg, col, c, nbuckets, [cur, en, ii, tn](u32 key, bool negate, u32 w) {
       u32 pos = B200_ATOMIC_ADD(&cur[key], 1u);
       en[pos] = ((u64)key << 32) | (u64)(((ii + w * tn) << 1) | (negate ? 1u : 0u));
-    });
+    }, only);
   }
 };
 
@@ -565,6 +582,70 @@ template <class C, class X = SeqExec> struct CombineBody {
   }
 };
 
+#if defined(__CUDACC__) && !defined(B200_EMULATE)
+#define B200_LANE_TAIL 1
+// ---- warp-cooperative tail kernels for ed25519 (lanefield.cuh) -------------------------------------
+// Horner over a column's windows, one WARP per column: the c doublings between two windows run on
+// lane-sliced coordinates (one coordinate per 8-lane group, limbs across lanes), the window sum is
+// added with the quad-lane schedule on the replicated point.
+struct CombineLaneBody {
+  static constexpr int kBlock = 32;
+  typedef Ed25519 C;
+  const C::Point* S;
+  const ColumnDesc* cols;
+  u32 c;
+  C::Point* out;
+  __device__ void operator()(u64 tid) const {
+    const u64 j = tid >> 5;
+    const ColumnDesc col = cols[j];
+    if (col.num_windows == 0 || col.n == 0) {
+      if ((tid & 31u) == 0)
+        out[j] = C::identity();
+      return;
+    }
+    const u32 nw = bucket_windows(col);
+    C::Point acc = S[col.first_window + nw - 1];
+    for (u32 w = nw - 1; w-- > 0;) {
+      u32 v = lane8::slice_point(acc);
+      v = lane8::dbl_n(v, (int)c);
+      lane8::gather_point(acc, v);
+      C::add<QuadExecConv>(acc, acc, S[col.first_window + w]);
+    }
+    if ((tid & 31u) == 0)
+      out[j] = acc;
+  }
+};
+// ristretto255 encoding with the inverse-square-root chain on 8 lanes per output
+struct LanePow {
+  static __device__ __forceinline__ void pow22523(F25519::E& r, const F25519::E& a) {
+    lane8::gather(r, lane8::pow22523(lane8::slice(a)));
+  }
+};
+struct StoreLaneBody {
+  static constexpr int kBlock = 32;
+  const Ed25519::Point* pts;
+  unsigned char* out;
+  u64 count;
+  __device__ void operator()(u64 tid) const {
+    const u64 i = tid >> 3;
+    const bool live = i < count;  // surplus lanes of the last warp compute along (warp-wide ballots)
+    unsigned char enc[32];
+    Ed25519::encode<LanePow>(enc, pts[live ? i : count - 1]);
+    if (live && (tid & 7u) == 0) {
+      uint4* d = (uint4*)(out + 32 * i);
+      const uint4* e = (const uint4*)enc;
+      d[0] = e[0];
+      d[1] = e[1];
+    }
+  }
+};
+#endif
+
+// canonical commitments of `count` accumulator points
+template <class C>
+inline void launch_store_commit(stream_t s, const typename C::Point* pts, unsigned char* out,
+                                u64 count, bool lane_tail = true);
+
 // generator ingestion (ABI layout -> device layout)
 template <class C, bool kProjective> struct IngestBody {
   static constexpr int kBlock = 128;
@@ -652,6 +733,19 @@ template <class C, bool kCommit> struct StoreBody {
       C::store_proj_abi(out + i * C::kAbiProjBytes, pts[i]);
   }
 };
+template <class C>
+inline void launch_store_commit(stream_t s, const typename C::Point* pts, unsigned char* out,
+                                u64 count, bool lane_tail) {
+#ifdef B200_LANE_TAIL
+  if constexpr (C::kCurveId == kRistretto255) {
+    if (lane_tail && count && count <= 4096) {  // latency-bound: 8 lanes per output
+      launch(StoreLaneBody{pts, out, count}, (count * 8 + 31) / 32 * 32, s);
+      return;
+    }
+  }
+#endif
+  launch(StoreBody<C, true>{pts, out}, count, s);
+}
 template <class C> struct GenToProjBody {  // device generators back to the projective ABI layout
   static constexpr int kBlock = 64;
   const typename C::Gen* gens;
@@ -808,8 +902,15 @@ void msm_accumulate_range(stream_t s, const MsmPlan& plan, const typename C::Gen
     copy_d2d(d_starts, d_counts, (nkeys + 1) * sizeof(u32), s);
   }
   u64* d_entries = (u64*)dev_alloc(slots_max * sizeof(u64), s);
-  launch(ScatterBody{d_cols, d_col_start, ncols, c, nbuckets, d_counts, d_entries}, total_terms,
-         s);
+  u32 max_windows = 0;
+  for (u32 j = 0; j < ncols; ++j)
+    max_windows = std::max(max_windows, cols[j].n ? cols[j].num_windows : 0u);
+  if (opt.scatter_window_major && max_windows > 1)
+    launch(ScatterBody{d_cols, d_col_start, ncols, c, nbuckets, d_counts, d_entries, total_terms},
+           total_terms * max_windows, s);
+  else
+    launch(ScatterBody{d_cols, d_col_start, ncols, c, nbuckets, d_counts, d_entries, 0},
+           total_terms, s);
   // d_counts[k] is now the END offset of bucket k's real entries
   if (L)
     launch(FillPadsBody{d_starts, d_counts, d_entries}, nkeys, s);
@@ -1011,6 +1112,17 @@ void msm_finish(stream_t s, const MsmPlan& plan, const typename C::Point* d_buck
   bool uniform_windows = true;  // same Horner trip count in every quad of a warp
   for (u32 j = 1; j < ncols; ++j)
     uniform_windows = uniform_windows && bucket_windows(plan.cols[j]) == bucket_windows(plan.cols[0]);
+#ifdef B200_LANE_TAIL
+  bool lane_done = false;
+  if constexpr (C::kCurveId == kRistretto255) {
+    if (ncols <= 2048 && opt.lane_tail) {  // one warp per column
+      launch(CombineLaneBody{d_S, d_cols, plan.c, out}, (u64)ncols * 32, s);
+      lane_done = true;
+    }
+  }
+  if (lane_done) {
+  } else
+#endif
   if (ncols <= opt.quad_threshold && uniform_windows)
     launch(CombineBody<C, QuadExecConv>{d_S, d_cols, plan.c, out}, (u64)ncols * QuadExec::kLanes,
            s);

@@ -222,6 +222,10 @@ void b200_combine_partials_projective_device(unsigned curve_id, void* out_res,
  * *_p2 structs (projective != 0, handle input) or affine structs at the commitment stride. */
 void b200_synthetic_generators_device(unsigned curve_id, void* out_generators, uint64_t n,
                                       uint64_t first, int projective);
+/* Self-test of the warp-cooperative (lane-sliced) field arithmetic of the tail kernels against the
+ * per-thread arithmetic on `warps` warps of pseudo-random and edge-case operands: returns the number
+ * of mismatching checks (0 = pass). */
+unsigned b200_selftest_lane_arithmetic(unsigned warps, unsigned seed);
 /* Per-launch CUDA-event timing of the dominant kernel (level-1 bucket accumulation) on the library
  * stream: enable, run, then read the total milliseconds and launch count since the last read. */
 void b200_profile_accumulate(int enable);

@@ -191,3 +191,7 @@ def generators_from_reference_table(curve_id, path):
     lib().emul_ingest_compact(C.c_uint(curve_id), C.c_void_p(table.ctypes.data), C.c_uint(w),
                               C.c_uint64(n), C.c_void_p(out.ctypes.data))
     return out
+
+
+def set_scatter_window_major(on=0):
+    lib().emul_set_scatter_window_major(C.c_uint(on))

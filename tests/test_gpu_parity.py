@@ -394,3 +394,20 @@ print("builtin table ok")
     r = subprocess.run([sys.executable, "-c", script, root], cwd=root, capture_output=True, text=True,
                        timeout=600)
     assert r.returncode == 0 and "builtin table ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_lane_sliced_field_arithmetic_selftest(bb):
+    """The warp-cooperative field arithmetic of the tail kernels (8 lanes per element, carries across
+    lanes by shuffle + ballot) against the per-thread schedules, on random and edge-case operands."""
+    for seed in (1, 2, 3):
+        assert bb.selftest_lane_arithmetic(256, seed) == 0, seed
+
+
+def test_lane_tail_on_off_agree(bb, port, monkeypatch):
+    rng = np.random.default_rng(123)
+    n = 3000
+    cols = common.random_columns(rng, n, [(0, 32, 0), (-100, 16, 1), (0, 1, 0), (-2999, 8, 0), (0, 5, 0)])
+    want = port.commit(0, cols, None, 9)
+    for flag in ("0", "1"):
+        monkeypatch.setenv("BLITZAR_B200_LANE_TAIL", flag)
+        assert np.array_equal(bb.compute_pedersen_commitments(0, cols, None, 9), want), flag
