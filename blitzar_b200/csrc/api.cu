@@ -201,7 +201,7 @@ private:
   // order of 100 cores and one core moves ~10 GB/s, PCIe 5 x16 wants ~55 GB/s
   const int kWorkers = [] {
     const char* env = std::getenv("BLITZAR_B200_STAGER_THREADS");
-    const int v = env ? std::atoi(env) : 8;
+    const int v = env ? std::atoi(env) : 4;  // measured on the B200 host: 2: 16.0, 4: 8.0, 8: 12.4, 16: 9.2 ms (n = 2^20)
     return std::max(1, std::min(32, v));
   }();
   unsigned char* staging_[kSlots] = {};
@@ -356,6 +356,11 @@ void commit_on(const State& st, unsigned curve_id, void* commitments, uint32_t n
   uint32_t num_ranges = (uint32_t)std::min<uint64_t>(n >> 18, num == 1 ? 8 : 4);
   if (num == 1 && n >= (1ull << 18))
     num_ranges = std::max(num_ranges, 2u);
+  // the Weierstrass curves pay a fixed latency per piece and batch-affine level (one Fermat inversion
+  // at the top of each inversion tree, 0.2-0.6 ms): pieces of >= 2^20 terms (bls12-381 n = 2^22 from
+  // pinned memory: 52.0 ms with 8 pieces)
+  if (curve_id != SXT_CURVE_RISTRETTO255)
+    num_ranges = (uint32_t)std::min<uint64_t>(n >> 20, 4);
   num_ranges = std::max(num_ranges, 1u);
   if (const char* env = std::getenv("BLITZAR_B200_RANGES"))
     num_ranges = (uint32_t)std::max(1, std::min(16, std::atoi(env)));
@@ -860,14 +865,10 @@ int sxt_ristretto255_get_generators(struct sxt_ristretto255* generators, uint64_
     return 1;
   const CurveVTable& V = kVTableEd25519;
   cudaStream_t s = g_state.stream;
-  DevBuf<unsigned char> gens(num_generators * V.gen_bytes, s);
-  const void* src = gens.p;
-  if (offset_generators + num_generators <= g_state.num_builtin)
-    src = (const unsigned char*)g_state.builtin + offset_generators * V.gen_bytes;
-  else
-    launch_builtin_generators(ctx(), gens.p, offset_generators, num_generators);
+  // generated straight into the ABI layout: the exact (X : Y : Z : T) of the derivation
+  // (sqcgn::compute_base_element), not a round trip through the cached generator form
   DevBuf<unsigned char> out(num_generators * V.abi_proj_bytes, s);
-  V.gens_to_projective(ctx(), src, out.p, num_generators);
+  V.synth_generators(ctx(), out.p, num_generators, offset_generators, true);
   copy_d2h(generators, out.p, num_generators * V.abi_proj_bytes, s);
   stream_sync(s);
   return 0;

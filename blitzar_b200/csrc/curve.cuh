@@ -13,7 +13,6 @@
 // d non-square); short Weierstrass a=0 complete formulas (Renes-Costello-Batina 2016, Alg. 7/8/9).
 #pragma once
 #include "field.cuh"
-#include "fp64field.cuh"
 
 namespace b200 {
 
@@ -164,7 +163,7 @@ struct Ed25519 {
     X::template mul4<F>(o.X, o.Y, o.T, o.Z, E, Fv, G, H, E, H, Fv, G);
     r = o;
   }
-  // coordinates are stored canonical (< p) so the FP64 accumulation path can take 51-bit limbs
+  // coordinates are stored canonical (< p)
   static B200_HD void point_to_gen(Gen& g, const Point& p) {
     F::add(g.YpX, p.Y, p.X);
     F::sub(g.YmX, p.Y, p.X);
@@ -185,101 +184,6 @@ struct Ed25519 {
     a.Z = F::one();
     F::mul(a.T, a.X, a.Y);
     point_to_gen(g, a);
-  }
-  // ---- FP64-pipe accumulator (see fp64field.cuh) --------------------------------------------------
-  // Exact and parity-green on B200 (all GPU tests pass with it), but NOT faster: measured
-  // (tests/micro/latency.cu) 82.8 SM-cycles per warp-multiplication against 82.9 for the integer
-  // carry-chain schedule, 852 vs 808 per point addition — the exact split costs ~330 issue slots
-  // per multiplication (bit-pattern accumulation, conversions), which makes it issue-bound where the
-  // integer schedule is multiplier-pipe-bound. Kept, disabled, as the measured alternative.
-  static constexpr bool kFp64Accumulate = false;
-  struct AccD {
-    FeD X, Y, Z, T;
-  };
-  static B200_HD void to_doubles(double* d, const FeD& a) {
-#pragma unroll
-    for (int i = 0; i < 5; ++i)
-      d[i] = F25519D::to_double(a.l[i]);
-  }
-  static B200_HD void accd_from_gen(AccD& r, const Gen& g, bool negate) {
-    FeD yp, ym, z2, t2d, invd;
-    F25519D::from_fe(yp, g.YpX);
-    F25519D::from_fe(ym, g.YmX);
-    F25519D::from_fe(z2, g.Z2);
-    F25519D::from_fe(t2d, g.T2d);
-    F25519D::from_fe(invd, F::constant([](int i) { return F25_INVD(i); }));
-    i64 x[5], y[5], z[5];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      x[i] = yp.l[i] - ym.l[i];
-      y[i] = yp.l[i] + ym.l[i];
-      z[i] = z2.l[i];
-    }
-    double dt[5], dk[5];
-    to_doubles(dt, t2d);
-    to_doubles(dk, invd);
-    F25519D::mul(r.T, dt, dk);
-    F25519D::carry(r.X, x);
-    F25519D::carry(r.Y, y);
-    F25519D::carry(r.Z, z);
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      r.X.l[i] = negate ? -r.X.l[i] : r.X.l[i];
-      r.T.l[i] = negate ? -r.T.l[i] : r.T.l[i];
-    }
-  }
-  // a += (negate ? -g : g): the 8-multiplication cached-form addition with the products on the
-  // FP64 pipe; lazy additions are exact double additions of converted limbs
-  static B200_HD void accd_add_gen(AccD& a, const Gen& g, bool negate) {
-    FeD yp, ym, z2, t2d;
-    F25519D::from_fe(yp, g.YpX);
-    F25519D::from_fe(ym, g.YmX);
-    F25519D::from_fe(z2, g.Z2);
-    F25519D::from_fe(t2d, g.T2d);
-    double qp[5], qm[5], qz[5], qt[5], x1[5], y1[5], z1[5], t1[5], t0[5], s1[5];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      qp[i] = F25519D::to_double(negate ? ym.l[i] : yp.l[i]);
-      qm[i] = F25519D::to_double(negate ? yp.l[i] : ym.l[i]);
-      qz[i] = F25519D::to_double(z2.l[i]);
-      qt[i] = F25519D::to_double(negate ? -t2d.l[i] : t2d.l[i]);
-    }
-    to_doubles(x1, a.X);
-    to_doubles(y1, a.Y);
-    to_doubles(z1, a.Z);
-    to_doubles(t1, a.T);
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      t0[i] = y1[i] - x1[i];
-      s1[i] = y1[i] + x1[i];
-    }
-    FeD A, B, C, D;
-    F25519D::mul(A, t0, qm);
-    F25519D::mul(B, s1, qp);
-    F25519D::mul(C, t1, qt);
-    F25519D::mul(D, z1, qz);
-    double da[5], db[5], dc[5], dd[5], e[5], f[5], gg[5], h[5];
-    to_doubles(da, A);
-    to_doubles(db, B);
-    to_doubles(dc, C);
-    to_doubles(dd, D);
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      e[i] = db[i] - da[i];
-      f[i] = dd[i] - dc[i];
-      gg[i] = dd[i] + dc[i];
-      h[i] = db[i] + da[i];
-    }
-    F25519D::mul(a.X, e, f);
-    F25519D::mul(a.Y, gg, h);
-    F25519D::mul(a.T, e, h);
-    F25519D::mul(a.Z, f, gg);
-  }
-  static B200_HD void accd_to_point(Point& p, const AccD& a) {
-    F25519D::to_fe(p.X, a.X);
-    F25519D::to_fe(p.Y, a.Y);
-    F25519D::to_fe(p.Z, a.Z);
-    F25519D::to_fe(p.T, a.T);
   }
   // (2X : 2Y : 2Z : 2T) — the same point; one multiplication by the constant 1/d
   static B200_HD void gen_to_point(Point& r, const Gen& g, bool negate) {
@@ -547,7 +451,6 @@ template <class FieldT, class CP> struct Weierstrass {
   static constexpr int kAbiProjBytes = 3 * 4 * N;            // {X,Y,Z}
   static constexpr int kAbiCommitBytes = CP::kAbiCommitBytes;
 
-  static constexpr bool kFp64Accumulate = false;
   static constexpr bool kBatchAffine = true;  // batch_affine.cuh
   struct Point {
     fe X, Y, Z;

@@ -11,7 +11,7 @@ unsigned selftest_lane_arithmetic(const EngineCtx& ctx, unsigned warps, unsigned
 #ifdef B200_LANE_TAIL
   DevBuf<u32> bad(1, ctx.s);
   dev_zero(bad.p, sizeof(u32), ctx.s);
-  launch(lane8::SelfTestBody{seed, bad.p}, (u64)warps * 32, ctx.s);
+  launch(lane10::SelfTestBody{seed, bad.p}, (u64)warps * 32, ctx.s);
   u32 host = 0;
   copy_d2h(&host, bad.p, sizeof(u32), ctx.s);
   stream_sync(ctx.s);

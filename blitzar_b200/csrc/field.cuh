@@ -253,13 +253,7 @@ struct F25519 {
   }
   // production schedule: 64 wide multiply-adds on even/odd register pairs (mul_wide_eo), one
   // merge chain, then the 2^256 = 38 fold as a lo pass and a hi pass of mad.cc chains.
-  static B200_HD void mul(E& r, const E& a, const E& b) {
-#ifdef B200_F25519_KARATSUBA
-    mul_kara(r, a, b);
-#else
-    mul_school(r, a, b);
-#endif
-  }
+  static B200_HD void mul(E& r, const E& a, const E& b) { mul_school(r, a, b); }
   static B200_HD void mul_school(E& r, const E& a, const E& b) {
     u32 Ev[16], Ov[16], R[16];
     mul_wide_eo<8>(Ev, Ov, a.l, b.l);
@@ -291,67 +285,6 @@ struct F25519 {
     r.l[0] += 38u * c2;  // a wrap leaves a value < 2^12, so this cannot carry
   }
 
-  // x = s ? -x : x over N limbs (two's complement); returns the carry out of the negation chain
-  // (1 only for s = 1, x = 0)
-  template <int N> static B200_HD u32 cond_negate(u32* x, u32 s) {
-    const u32 mask = 0u - s;
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-      x[i] ^= mask;
-    x[0] = add_cc(x[0], s);
-#pragma unroll
-    for (int i = 1; i < N; ++i)
-      x[i] = addc_cc(x[i], 0u);
-    return addc(0u, 0u);
-  }
-  // E + (O << 32) of a 4x4-limb mul_wide_eo product -> 8 plain limbs
-  static B200_HD void merge_eo8(u32* z, const u32* Ev, const u32* Ov) {
-    z[0] = Ev[0];
-    z[1] = add_cc(Ev[1], Ov[0]);
-#pragma unroll
-    for (int k = 2; k < 7; ++k)
-      z[k] = addc_cc(Ev[k], Ov[k - 1]);
-    z[7] = addc(Ev[7], Ov[6]);
-  }
-  // One level of subtractive Karatsuba: 3 x 16 wide multiply-adds instead of 64, paid for with
-  // ~90 additions / logic ops on the ALU pipe (the multiplier pipe is the kernel's bound).
-  //   a*b = z0 + 2^128 (z0 + z2 + (a0-a1)(b1-b0)) + 2^256 z2
-  static B200_HD void mul_kara(E& r, const E& a, const E& b) {
-    u32 Ev[8], Ov[8], z0[8], z2[8], m[8], da[4], db[4];
-    mul_wide_eo<4>(Ev, Ov, a.l, b.l);
-    merge_eo8(z0, Ev, Ov);
-    mul_wide_eo<4>(Ev, Ov, a.l + 4, b.l + 4);
-    merge_eo8(z2, Ev, Ov);
-    const u32 sa = limbs_sub<4>(da, a.l, a.l + 4);  // a0 - a1
-    const u32 sb = limbs_sub<4>(db, b.l + 4, b.l);  // b1 - b0
-    cond_negate<4>(da, sa);
-    cond_negate<4>(db, sb);
-    mul_wide_eo<4>(Ev, Ov, da, db);
-    merge_eo8(m, Ev, Ov);
-    // t + top*2^256 = z0 + z2 +- m
-    const u32 s = sa ^ sb;
-    u32 t[8];
-    const u32 c1 = limbs_add<8>(t, z0, z2);
-    const u32 c3 = cond_negate<8>(m, s);
-    const u32 c2 = limbs_add<8>(t, t, m);
-    const u32 top = c1 + c2 + c3 - s;
-    u32 R[16];
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      R[k] = z0[k];
-    R[4] = add_cc(z0[4], t[0]);
-#pragma unroll
-    for (int k = 1; k < 4; ++k)
-      R[4 + k] = addc_cc(z0[4 + k], t[k]);
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      R[8 + k] = addc_cc(z2[k], t[4 + k]);
-    R[12] = addc_cc(z2[4], top);
-    R[13] = addc_cc(z2[5], 0u);
-    R[14] = addc_cc(z2[6], 0u);
-    R[15] = addc(z2[7], 0u);
-    fold_cc(r, R);
-  }
   static B200_HD void sqr(E& r, const E& a) { mul(r, a, a); }
 
   // latency-oriented schedule for the serial tail kernels (QuadExec): product scanning — the 15

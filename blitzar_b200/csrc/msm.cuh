@@ -320,23 +320,6 @@ template <class C> struct MergeBucketsBody {
   }
 };
 
-// Accumulator of the gathering level: the curve's Point, or its FP64-pipe form where the curve
-// provides one (ed25519).
-template <class C, class X, bool kFp64> struct GatherAcc {
-  typename C::Point p;
-  B200_HD void start(const typename C::Gen& g, bool negate) { C::gen_to_point(p, g, negate); }
-  B200_HD void add(const typename C::Gen& g, bool negate) {
-    C::template add_gen<X>(p, p, g, negate);
-  }
-  B200_HD void get(typename C::Point& out) const { out = p; }
-};
-template <class C, class X> struct GatherAcc<C, X, true> {
-  typename C::AccD a;
-  B200_HD void start(const typename C::Gen& g, bool negate) { C::accd_from_gen(a, g, negate); }
-  B200_HD void add(const typename C::Gen& g, bool negate) { C::accd_add_gen(a, g, negate); }
-  B200_HD void get(typename C::Point& out) const { C::accd_to_point(out, a); }
-};
-
 // Chunk walk. Thread t sums entries [t*K, (t+1)*K) of the sorted list. Segments (runs of one key)
 // strictly inside the chunk are complete and go straight to buckets[key]; the first and last
 // segment may continue in the neighbouring chunks, so they are emitted as pieces (2 per chunk,
@@ -400,7 +383,14 @@ template <class C, bool kGather, class X = SeqExec> struct AccumulateBody {
       u64 ent = entries[b];
       typename C::Gen g = gens[(u32)ent >> 1];
       cur = (u32)(ent >> 32);
-      GatherAcc<C, X, C::kFp64Accumulate> ga;
+      struct {
+        Point p;
+        B200_HD void start(const typename C::Gen& g, bool negate) { C::gen_to_point(p, g, negate); }
+        B200_HD void add(const typename C::Gen& g, bool negate) {
+          C::template add_gen<X>(p, p, g, negate);
+        }
+        B200_HD void get(Point& out) const { out = p; }
+      } ga;
       for (u64 i = b; i < e; ++i) {
         u64 ent_n = ent;
         typename C::Gen g_n = g;
@@ -603,22 +593,25 @@ struct CombineLaneBody {
         out[j] = C::identity();
       return;
     }
+    const lane10::Lane L = lane10::lane_info();
     const u32 nw = bucket_windows(col);
     C::Point acc = S[col.first_window + nw - 1];
     for (u32 w = nw - 1; w-- > 0;) {
-      u32 v = lane8::slice_point(acc);
-      v = lane8::dbl_n(v, (int)c);
-      lane8::gather_point(acc, v);
+      u32 t;
+      const u32 v = lane10::dbl_n(L, lane10::slice_point(L, acc), (int)c, t);
+      lane10::gather_point(acc, v, t);
       C::add<QuadExecConv>(acc, acc, S[col.first_window + w]);
     }
     if ((tid & 31u) == 0)
       out[j] = acc;
   }
 };
-// ristretto255 encoding with the inverse-square-root chain on 8 lanes per output
+// ristretto255 encoding with the inverse-square-root chain on 10 lanes per output, 3 outputs per warp
 struct LanePow {
   static __device__ __forceinline__ void pow22523(F25519::E& r, const F25519::E& a) {
-    lane8::gather(r, lane8::pow22523(lane8::slice(a)));
+    const lane10::Lane L = lane10::lane_info();
+    const u32 g = L.base / 10u;
+    lane10::gather(r, lane10::pow22523(L, lane10::slice(L, a)), g < 3 ? g : 0u);
   }
 };
 struct StoreLaneBody {
@@ -627,11 +620,12 @@ struct StoreLaneBody {
   unsigned char* out;
   u64 count;
   __device__ void operator()(u64 tid) const {
-    const u64 i = tid >> 3;
-    const bool live = i < count;  // surplus lanes of the last warp compute along (warp-wide ballots)
+    const u32 lane = (u32)tid & 31u, g = lane / 10u;
+    const u64 i = (tid >> 5) * 3 + g;
+    const bool live = g < 3 && i < count;  // surplus lanes compute along (warp-wide shuffles)
     unsigned char enc[32];
     Ed25519::encode<LanePow>(enc, pts[live ? i : count - 1]);
-    if (live && (tid & 7u) == 0) {
+    if (live && lane == 10u * g) {
       uint4* d = (uint4*)(out + 32 * i);
       const uint4* e = (const uint4*)enc;
       d[0] = e[0];
@@ -738,8 +732,8 @@ inline void launch_store_commit(stream_t s, const typename C::Point* pts, unsign
                                 u64 count, bool lane_tail) {
 #ifdef B200_LANE_TAIL
   if constexpr (C::kCurveId == kRistretto255) {
-    if (lane_tail && count && count <= 4096) {  // latency-bound: 8 lanes per output
-      launch(StoreLaneBody{pts, out, count}, (count * 8 + 31) / 32 * 32, s);
+    if (lane_tail && count && count <= 4096) {  // latency-bound: 10 lanes per output
+      launch(StoreLaneBody{pts, out, count}, (count + 2) / 3 * 32, s);
       return;
     }
   }

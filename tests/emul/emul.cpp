@@ -10,7 +10,6 @@
 // emul_prefix.h force-included and reached through the same type-erased vtables api.cu uses.
 #include "emul_prefix.h"
 #include "../../blitzar_b200/csrc/engine_api.cuh"
-#include "../../blitzar_b200/csrc/fp64field.cuh"
 
 using namespace b200;
 
@@ -171,9 +170,6 @@ extern "C" int emul_check_mul(unsigned field_id, unsigned iters, unsigned seed) 
       F25519::mul_lat(r1, a, b);
       F25519::canonical(c1, r1);
       for (int i = 0; i < 8; ++i) if (c1.l[i] != c2.l[i]) { ++bad; break; }
-      F25519::mul_kara(r1, a, b);
-      F25519::canonical(c1, r1);
-      for (int i = 0; i < 8; ++i) if (c1.l[i] != c2.l[i]) { ++bad; break; }
     }
     return bad;
   }
@@ -202,49 +198,6 @@ extern "C" void emul_combine_partials(unsigned curve_id, void* out_commitments, 
   std::vector<unsigned char> sum((size_t)count * V.point_bytes);
   V.sum_parts(ctx, partials, num_parts, count, sum.data());
   V.store(ctx, sum.data(), out_commitments, count, true);
-}
-
-// FP64-pipe field multiplication (exact integer semantics) vs the plain reference schedule
-extern "C" int emul_check_fp64(unsigned iters, unsigned seed) {
-  int bad = 0;
-  unsigned long long st = seed * 0x9E3779B97F4A7C15ull + 7;
-  auto next = [&st]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (u32)(st >> 16); };
-  for (unsigned it = 0; it < iters; ++it) {
-    F25519::E a, b, c, d, ca, cb, cc, cd, want, got;
-    for (int i = 0; i < 8; ++i) { a.l[i] = next(); b.l[i] = next(); c.l[i] = next(); d.l[i] = next(); }
-    if (it % 5 == 0) for (int i = 0; i < 8; ++i) a.l[i] = 0xffffffffu;
-    if (it % 7 == 0) for (int i = 0; i < 8; ++i) b.l[i] = 0;
-    if (it % 11 == 0) { for (int i = 0; i < 8; ++i) c.l[i] = 0xffffffffu; c.l[7] = 0x7fffffffu; c.l[0] = 0xffffffecu; }
-    F25519::canonical(ca, a); F25519::canonical(cb, b); F25519::canonical(cc, c); F25519::canonical(cd, d);
-    // (a - b) * (c + d) with lazy operands, as the point formulas use the multiplier
-    F25519::E s1, s2;
-    F25519::sub(s1, ca, cb); F25519::add(s2, cc, cd);
-    F25519::mul_ref(want, s1, s2); F25519::canonical(want, want);
-    FeD fa, fb, fc, fd, r;
-    F25519D::from_fe(fa, ca); F25519D::from_fe(fb, cb); F25519D::from_fe(fc, cc); F25519D::from_fe(fd, cd);
-    // balance the unsigned limbs first (as accumulator coordinates are)
-    long long ta[5], tb[5], tc[5], td[5];
-    for (int i = 0; i < 5; ++i) { ta[i] = fa.l[i]; tb[i] = fb.l[i]; tc[i] = fc.l[i]; td[i] = fd.l[i]; }
-    F25519D::carry(fa, ta); F25519D::carry(fb, tb); F25519D::carry(fc, tc); F25519D::carry(fd, td);
-    double x[5], y[5];
-    for (int i = 0; i < 5; ++i) {
-      x[i] = F25519D::to_double(fa.l[i]) - F25519D::to_double(fb.l[i]);
-      y[i] = F25519D::to_double(fc.l[i]) + F25519D::to_double(fd.l[i]);
-    }
-    F25519D::mul(r, x, y);
-    // chain a second multiplication on the balanced result
-    double z[5], w[5];
-    for (int i = 0; i < 5; ++i) { z[i] = F25519D::to_double(r.l[i]); w[i] = F25519D::to_double(fa.l[i]); }
-    FeD r2; F25519D::mul(r2, z, w);
-    F25519D::to_fe(got, r); F25519::canonical(got, got);
-    for (int i = 0; i < 8; ++i) if (got.l[i] != want.l[i]) { ++bad; break; }
-    F25519::E want2, got2;
-    F25519::mul_ref(want2, want, ca); F25519::canonical(want2, want2);
-    F25519D::to_fe(got2, r2); F25519::canonical(got2, got2);
-    for (int i = 0; i < 8; ++i) if (got2.l[i] != want2.l[i]) { ++bad; break; }
-    for (int i = 0; i < 5; ++i) if (r.l[i] > (1LL << 50) + (1LL << 14) || r.l[i] < -(1LL << 50) - (1LL << 14)) { ++bad; break; }
-  }
-  return bad;
 }
 
 // inner-product argument through the emulated kernels (same contracts as the sxt_* entry points)

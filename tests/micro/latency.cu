@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 #include "../../blitzar_b200/csrc/curve.cuh"
+#include "rejected_experiments.cuh"
 using namespace b200;
 
 template <int OP> __global__ void k_lat(Fe<8>* io, long long* cycles, int iters) {
@@ -36,7 +37,7 @@ template <int OP> __global__ void k_thr(Fe<8>* io, int iters) {
     if (OP == 0) F::mul(a, a, b);
     if (OP == 1) F::mul_lat(a, a, b);
     if (OP == 2) F::mul_ref(a, a, b);
-    if (OP == 3) F::mul_kara(a, a, b);
+    if (OP == 3) rejected::mul_kara(a, a, b);
   }
   if (a.l[0] == 0x12345678u) io[8] = a;
 }
@@ -63,9 +64,9 @@ __global__ void k_thr_fp64(Fe<8>* io, int iters) {
 __global__ void k_thr_accd(Fe<8>* io, int iters) {
   Ed25519::Gen g;
   F25519::canonical(g.YpX, io[0]); F25519::canonical(g.YmX, io[1]); F25519::canonical(g.Z2, io[2]); F25519::canonical(g.T2d, io[3]);
-  Ed25519::AccD acc;
-  Ed25519::accd_from_gen(acc, g, false);
-  for (int it = 0; it < iters; ++it) Ed25519::accd_add_gen(acc, g, (it & 1) != 0);
+  rejected::AccD acc;
+  rejected::accd_from_gen(acc, g, false);
+  for (int it = 0; it < iters; ++it) rejected::accd_add_gen(acc, g, (it & 1) != 0);
   if (acc.X.l[0] == 0x12345678) io[8].l[0] = (u32)acc.Y.l[1];
 }
 __global__ void k_thr_addgen(Fe<8>* io, int iters) {

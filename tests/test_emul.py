@@ -153,10 +153,6 @@ def test_generator_ranges_share_one_bucket_array(emul, port, curve, num_ranges):
         assert common.same(0, got_builtin, port.commit(0, cols[:2], None, 5))
 
 
-def test_fp64_pipe_multiplication_is_exact(emul):
-    """The (disabled, measured-not-faster) FP64-pipe multiplier keeps exact integer semantics."""
-    import ctypes as C
-    assert int(emul.lib().emul_check_fp64(C.c_uint(3000), C.c_uint(9))) == 0
 
 
 def test_column_groups_with_generator_ranges(emul, port):

@@ -397,8 +397,9 @@ print("builtin table ok")
 
 
 def test_lane_sliced_field_arithmetic_selftest(bb):
-    """The warp-cooperative field arithmetic of the tail kernels (8 lanes per element, carries across
-    lanes by shuffle + ballot) against the per-thread schedules, on random and edge-case operands."""
+    """The warp-cooperative field arithmetic of the tail kernels (10 lanes per element in radix 2^25.5,
+    carries across lanes by shuffle) against the per-thread schedules, on random and edge-case
+    operands."""
     for seed in (1, 2, 3):
         assert bb.selftest_lane_arithmetic(256, seed) == 0, seed
 
