@@ -171,6 +171,45 @@ struct IpaRoundColumnsBody {
   }
 };
 
+// verifier exponents g_i = ap * prod_j x_j^(+-1) (prfip::compute_verification_exponents,
+// sxt/proof/inner_product/verification_computation.cc:86-127): g_0 = ap * prod_j x_j^-1 and every set
+// bit t of i multiplies by x_(k-1-t)^2. One thread per i, at most k products; the multipliers are in
+// Montgomery form, so the values stay in plain form.
+struct IpaVerifyExponentsBody {
+  static constexpr int kBlock = 128;
+  ScE g0;            // plain form
+  const ScE* xsq_m;  // k squares of the challenges, Montgomery form
+  u32 k;
+  ScE* out;          // np entries
+  B200_HD void operator()(u64 i) const {
+    ScE g = g0;
+    for (u32 t = 0; t < k; ++t)
+      if ((i >> t) & 1u)
+        FS::mul(g, xsq_m[k - 1 - t], g);
+    out[i] = g;
+  }
+};
+// per-thread partial sums of <g, b> (each product carries a factor R^-1; slot 2t + 1 stays zero so
+// that IpaDotFinalBody can finish the sum)
+struct IpaDot1Body {
+  static constexpr int kBlock = 64;
+  const ScE* a;
+  const ScE* b;
+  u64 n;
+  u32 K;
+  ScE* partial;
+  B200_HD void operator()(u64 t) const {
+    ScE acc = FS::zero(), p;
+    const u64 b0 = t * K, e0 = b0 + K < n ? b0 + K : n;
+    for (u64 i = b0; i < e0; ++i) {
+      FS::mul(p, a[i], b[i]);
+      FS::add(acc, acc, p);
+    }
+    partial[2 * t] = acc;
+    partial[2 * t + 1] = FS::zero();
+  }
+};
+
 struct Ipa {
   typedef Ed25519 C;
   typedef CurveOps<C> Ops;
@@ -354,39 +393,48 @@ struct Ipa {
     for (unsigned j = 0; j < k; ++j)
       x[j] = round_challenge(tr, l_vector + 32 * j, r_vector + 32 * j);
     // exponents: [product', g_0 .. g_{np-1}, -x_j^2 ..., -x_j^-2 ...]
-    // (prfip::compute_verification_exponents, verification_computation.cc:86-127)
+    // (prfip::compute_verification_exponents, verification_computation.cc:86-127), built in HBM: the
+    // host computes only the 2k + 1 values that depend on the challenges alone
     const uint64_t num = 1 + np + 2 * k;
-    std::vector<uint8_t> e(32 * num);
+    DevBuf<ScE> e(num + 1, s);
     const Sc ap = sc_load(ap_value);
     if (n == 1) {
-      sc_store(&e[0], sc_mul(sc_load(b_vector), ap));
-      sc_store(&e[32], ap);
+      uint8_t e2[64];
+      sc_store(e2, sc_mul(sc_load(b_vector), ap));
+      sc_store(e2 + 32, ap);
+      copy_h2d(e.p, e2, 64, s);
+      stream_sync(s);
     } else {
       Sc allinv = sc_one();
-      std::vector<Sc> xsq(k);
+      std::vector<uint8_t> tail(64 * k), xsq_m(32 * k);
       for (unsigned j = 0; j < k; ++j) {
-        Sc xi = sc_inv(x[j]);
+        const Sc xi = sc_inv(x[j]);
         allinv = sc_mul(allinv, xi);
-        xsq[j] = sc_mul(x[j], x[j]);
-        sc_store(&e[32 * (1 + np + j)], sc_neg(xsq[j]));
-        sc_store(&e[32 * (1 + np + k + j)], sc_neg(sc_mul(xi, xi)));
+        const Sc xs = sc_mul(x[j], x[j]);
+        sc_store(&tail[32 * j], sc_neg(xs));
+        sc_store(&tail[32 * (k + j)], sc_neg(sc_mul(xi, xi)));
+        sc_store(&xsq_m[32 * j], sc_to_mont(xs));
       }
-      // g_i = ap * prod_j x_j^(+-1): bit t of i (t = 0 least significant) selects x_{k-1-t}
-      std::vector<Sc> g(np);
-      g[0] = sc_mul(allinv, ap);
-      uint64_t filled = 1;
-      for (unsigned t = 0; t < k; ++t) {
-        const Sc m = sc_to_mont(xsq[k - 1 - t]);
-        for (uint64_t i = 0; i < filled; ++i)
-          g[filled + i] = sc_mul_mont(m, g[i]);
-        filled *= 2;
+      DevBuf<ScE> d_xsq(k, s), d_b(n, s);
+      copy_h2d(d_xsq.p, xsq_m.data(), 32 * k, s);
+      copy_h2d(e.p + 1 + np, tail.data(), 64 * k, s);
+      copy_h2d(d_b.p, b_vector, 32 * n, s);
+      launch(IpaReduceBody{d_b.p}, n, s);
+      ScE g0;
+      {
+        const Sc g0s = sc_mul(allinv, ap);
+        for (int i = 0; i < 4; ++i) {
+          g0.l[2 * i] = (u32)g0s.v[i];
+          g0.l[2 * i + 1] = (u32)(g0s.v[i] >> 32);
+        }
       }
-      Sc prod = sc_zero();
-      for (uint64_t i = 0; i < n; ++i)
-        prod = sc_muladd(g[i], sc_load(b_vector + 32 * i), prod);
-      sc_store(&e[0], prod);
-      for (uint64_t i = 0; i < np; ++i)
-        sc_store(&e[32 * (1 + i)], g[i]);
+      launch(IpaVerifyExponentsBody{g0, d_xsq.p, k, e.p + 1}, np, s);
+      const u32 K = 64;
+      const uint64_t T = (n + K - 1) / K;
+      DevBuf<ScE> partial(2 * T + 2, s), scratch(1, s);
+      launch(IpaDot1Body{e.p + 1, d_b.p, n, K, partial.p}, T, s);
+      launch(IpaDotFinalBody{partial.p, T, e.p, scratch.p}, 2, s);
+      stream_sync(s);  // the host staging vectors and the DevBufs of this scope end here
     }
     // generators: [Q, G_0 .. G_{np-1}, L_j ..., R_j ...]
     DevBuf<C::Gen> gstore(np + 1, s);
@@ -404,7 +452,22 @@ struct Ipa {
       stream_sync(s);  // lr is freed (stream-ordered) after the kernel
     }
     uint8_t expected[32], commit[32];
-    msm_compressed(ctx, expected, gens.p, num, &e[0], nullptr, nullptr);
+    {
+      std::vector<ColumnDesc> cols(1);
+      cols[0].base = (const unsigned char*)e.p;
+      cols[0].row_stride = 32;
+      cols[0].bit_offset = 0;
+      cols[0].bit_width = 256;
+      cols[0].n = (u32)num;
+      cols[0].is_signed = 0;
+      cols[0].first_window = cols[0].num_windows = 0;
+      DevBuf<C::Point> pt(1, s);
+      DevBuf<unsigned char> enc(32, s);
+      Ops::run_columns(ctx, gens.p, cols, pt.p);
+      launch_store_commit<C>(s, pt.p, enc.p, 1, ctx.opt.lane_tail != 0);
+      copy_d2h(expected, enc.p, 32, s);
+      stream_sync(s);
+    }
     // commit = product * Q + a_commit
     DevBuf<unsigned char> araw(C::kAbiGenBytes, s);
     DevBuf<C::Gen> pair(2, s);
