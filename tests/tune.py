@@ -12,9 +12,7 @@ rng = np.random.default_rng(0)
 if curve == 0:
     gens = bb.get_generators(n, 0)
 else:
-    from oracle import port
-    base = port.test_points(curve, 512, 1)[1]
-    gens = np.tile(base, (n // 512 + 1, 1))[:n].copy()
+    gens = bb.synthetic_generators(curve, n, 0, projective=False)  # distinct points
 s = rng.integers(0, 256, (n, 32), dtype=np.uint8)
 s[:, 31] &= 0x0f
 dg = bb.DeviceBuffer(host=gens); ds = bb.DeviceBuffer(host=s); do = bb.DeviceBuffer(256)
@@ -30,7 +28,8 @@ def run(iters=5):
     return best
 
 ref = None
-grid = [(c, k1, kn, g1, gn) for c in (13, 14, 15, 16) for k1 in (16, 32) for kn in (8,) for g1, gn in ((8, 8), (32, 8), (16, 4))]
+grid = [(c, k1, kn, g1, gn) for c in (0, 15) for k1 in (0, 48, 96) for kn in (8, 4, 16)
+        for g1, gn in ((16, 4), (8, 4), (32, 4), (16, 8), (8, 8), (8, 2), (4, 4), (32, 8))]
 if len(sys.argv) > 3:
     grid = [tuple(int(x) for x in a.split(',')) for a in sys.argv[3:]]
 for c, k1, kn, g1, gn in grid:
