@@ -17,5 +17,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:AccumulateBody -c 1 -o gpurun_out/k_accumulate python tests/prof_c2.py 20 1 0 > gpurun_out/k_ncu_full.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/k_launches_bls.csv python tests/prof_c2.py 22 1 1 > /dev/null 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:PairPass2 -c 1 -o gpurun_out/k_pair_bls python tests/prof_c2.py 22 1 1 > gpurun_out/k_ncu_full_bls.log 2>&1
-bash tests/sanitizer.sh
+bash tests/scripts/sanitizer.sh
 ls -la gpurun_out/k_* gpurun_out/sanitizer_*
