@@ -356,11 +356,11 @@ void commit_on(const State& st, unsigned curve_id, void* commitments, uint32_t n
   uint32_t num_ranges = (uint32_t)std::min<uint64_t>(n >> 18, num == 1 ? 8 : 4);
   if (num == 1 && n >= (1ull << 18))
     num_ranges = std::max(num_ranges, 2u);
-  // the Weierstrass curves pay a fixed latency per piece and batch-affine level (one Fermat inversion
-  // at the top of each inversion tree, 0.2-0.6 ms): pieces of >= 2^20 terms (bls12-381 n = 2^22 from
-  // pinned memory: 52.0 ms with 8 pieces)
+  // the Weierstrass curves pay a fixed cost per piece and batch-affine level (inversion trees, scratch
+  // bucket merge): pieces of >= 2^21 terms. bls12-381 n = 2^22 from pinned memory, 1 / 2 / 3 / 4 / 8
+  // pieces: 42.4 / 41.4 / 46.1 / 46.3 / 52.0 ms (tests/e2e_c3_ranges.py)
   if (curve_id != SXT_CURVE_RISTRETTO255)
-    num_ranges = (uint32_t)std::min<uint64_t>(n >> 20, 4);
+    num_ranges = (uint32_t)std::min<uint64_t>(n >> 21, 4);
   num_ranges = std::max(num_ranges, 1u);
   if (const char* env = std::getenv("BLITZAR_B200_RANGES"))
     num_ranges = (uint32_t)std::max(1, std::min(16, std::atoi(env)));

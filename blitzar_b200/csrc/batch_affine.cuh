@@ -64,14 +64,14 @@ template <class F> struct BatchDownBody {
     }
   }
 };
-// top of the tree: at most kBatchTop values, one Fermat inversion per thread (all in parallel: the
-// latency of ONE inversion, without a serial prefix / back-substitution pass around it)
+// top of the tree: at most kBatchTop values, one inversion per thread (binary extended Euclid, all in
+// parallel: the latency of ONE inversion, without a serial prefix / back-substitution pass around it)
 template <class F> struct BatchTopBody {
   static constexpr int kBlock = 32;
   typename F::E* vals;
   B200_HD void operator()(u64 i) const {
     typename F::E inv;
-    F::invert(inv, vals[i]);
+    F::invert_eea(inv, vals[i]);  // at most kBatchTop threads: latency of one inversion
     vals[i] = inv;
   }
 };

@@ -136,6 +136,8 @@ template <class C> struct CurveOps {
     if (!pts)
       pts = tmp.p;
     EngineCtx rctx = ctx;
+    if (n && !generators_dev && !hook.builtin && ctx.builtin_windows > 1)
+      rctx.opt.gens_normalized = 1u;  // the built-in table's entries are normalised (Z = 1)
     // built-in generators covered by the precomputed fixed-base table (sxt_config::
     // num_precomputed_generators): shared-bucket table mode when it is the cheaper run
     if (n && !generators_dev && !hook.builtin &&
@@ -186,15 +188,14 @@ template <class C> struct CurveOps {
     DevBuf<Point> tmp(out_partials ? 1 : (num_outputs ? num_outputs : 1), s);
     if (!pts)
       pts = tmp.p;
+    EngineCtx tctx = ctx;
+    tctx.opt.gens_normalized = h->windows > 1 ? 1u : 0u;  // build_table normalised every entry
     if (prefer_table(cols, h->window_bits, h->windows, ctx.opt)) {
-      EngineCtx tctx = ctx;
       tctx.opt.window_bits = h->window_bits;
       for (auto& col : cols)
         col.table_n = h->n;
-      run_columns(tctx, (const Gen*)h->gens, cols, pts);
-    } else {
-      run_columns(ctx, (const Gen*)h->gens, cols, pts);
     }
+    run_columns(tctx, (const Gen*)h->gens, cols, pts);
     if (out_res)
       launch(StoreBody<C, false>{pts, (unsigned char*)out_res}, num_outputs, s);
   }

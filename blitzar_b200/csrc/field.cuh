@@ -716,6 +716,76 @@ template <class P> struct Mont {
   // r = 1/a (0 -> 0), Montgomery domain preserved
   static B200_HD void invert(E& r, const E& a) { pow(r, a, ExpPm2{}); }
 
+  // r = 1/a (0 -> 0), Montgomery domain preserved, by the binary extended Euclidean algorithm: about
+  // 2 * bits halving / subtraction steps of N-limb shifts and additions instead of the ~1.5 * bits field
+  // multiplications of the Fermat power — an order of magnitude less latency for ONE dependent
+  // inversion (the affine conversion of an output point, the top of a batch-inversion tree). Control
+  // flow depends on the data, so the throughput kernels (one inversion per thread of a full grid) keep
+  // invert().
+  static B200_HD void invert_eea(E& r, const E& a) {
+    if (is_zero(a)) {
+      r = zero();
+      return;
+    }
+    const E p = modulus();
+    E u = a, v = p, b = zero(), c = zero();
+    b.l[0] = 1u;
+    // invariants: b * a == u, c * a == v (mod p); u, v odd after the halving loops
+    for (;;) {
+      while (!(u.l[0] & 1u)) {
+        shr1(u, 0u);
+        halve_mod(b, p);
+      }
+      if (is_plain_one(u))
+        break;
+      while (!(v.l[0] & 1u)) {
+        shr1(v, 0u);
+        halve_mod(c, p);
+      }
+      if (is_plain_one(v))
+        break;
+      E d;
+      if (limbs_sub<N>(d.l, u.l, v.l) == 0) {  // u >= v
+        u = d;
+        sub(b, b, c);
+      } else {
+        limbs_sub<N>(v.l, v.l, u.l);
+        sub(c, c, b);
+      }
+    }
+    E y = is_plain_one(u) ? b : c;
+    // y = (a R)^-1 = a^-1 R^-1 as a plain residue; two Montgomery products by R^2 give a^-1 R
+    E r2;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      r2.l[i] = P::r2(i);
+    mul(y, y, r2);
+    mul(r, y, r2);
+  }
+  static B200_HD bool is_plain_one(const E& x) {
+    u32 t = x.l[0] ^ 1u;
+#pragma unroll
+    for (int i = 1; i < N; ++i)
+      t |= x.l[i];
+    return t == 0;
+  }
+  static B200_HD void shr1(E& x, u32 top_bit) {
+#pragma unroll
+    for (int i = 0; i < N - 1; ++i)
+      x.l[i] = (x.l[i] >> 1) | (x.l[i + 1] << 31);
+    x.l[N - 1] = (x.l[N - 1] >> 1) | (top_bit << 31);
+  }
+  // x / 2 mod p for x < p
+  static B200_HD void halve_mod(E& x, const E& p) {
+    if (x.l[0] & 1u) {
+      E t;
+      const u32 cy = limbs_add<N>(t.l, x.l, p.l);
+      x = t;
+      shr1(x, cy);
+    } else {
+      shr1(x, 0u);
+    }
+  }
   static B200_HD void from_mont(E& r, const E& a) {
     E o = zero();
     o.l[0] = 1;

@@ -340,6 +340,7 @@ template <class C, bool kGather, class X = SeqExec> struct AccumulateBody {
   u32* out_keys;
   Point* out_pieces;
   u32* out_m_ptr;
+  u32 unit_z;  // level 1: every generator is normalised (fixed-base table) — 7M additions on ed25519
 
   // every bucket is written exactly once per generator range (a run strictly inside a chunk is
   // complete; split runs travel down the cascade and are written by the level that completes them)
@@ -385,12 +386,14 @@ template <class C, bool kGather, class X = SeqExec> struct AccumulateBody {
       cur = (u32)(ent >> 32);
       struct {
         Point p;
+        bool unit;
         B200_HD void start(const typename C::Gen& g, bool negate) { C::gen_to_point(p, g, negate); }
         B200_HD void add(const typename C::Gen& g, bool negate) {
-          C::template add_gen<X>(p, p, g, negate);
+          C::template add_gen<X>(p, p, g, negate, unit);
         }
         B200_HD void get(Point& out) const { out = p; }
       } ga;
+      ga.unit = unit_z != 0;
       for (u64 i = b; i < e; ++i) {
         u64 ent_n = ent;
         typename C::Gen g_n = g;
@@ -658,8 +661,8 @@ template <class C, bool kProjective> struct IngestBody {
 // partition_table.h:36-98 — the reference tabulates all 2^w subset sums of w-generator groups; here
 // the table holds 2^(c w) G_i for every window w, normalised to Z = 1, so that all windows of a
 // fixed-base MSM share one bucket set and the Horner tail disappears). table[0 .. n) holds the
-// generators on entry; thread i fills table[w n + i], w = 1 .. W-1, with one inversion
-// (Montgomery's trick over its W-1 points).
+// generators on entry; thread i fills table[w n + i], w = 0 .. W-1 (window 0 = the generator itself,
+// normalised too), with one inversion (Montgomery's trick over its W points).
 constexpr int kMaxTableWindows = 33;  // c >= 8
 template <class C> struct PrecomputeTableBody {
   static constexpr int kBlock = 64;
@@ -671,15 +674,16 @@ template <class C> struct PrecomputeTableBody {
     typename C::Point p, pts[kMaxTableWindows];
     typename F::E prefix[kMaxTableWindows], acc = F::one(), inv;
     C::gen_to_point(p, table[i], false);
-    for (u32 w = 1; w < W; ++w) {
-      for (u32 k = 0; k < c; ++k)
-        C::dbl(p, p);
+    for (u32 w = 0; w < W; ++w) {  // window 0 (the generator itself) is normalised as well
+      if (w)
+        for (u32 k = 0; k < c; ++k)
+          C::dbl(p, p);
       pts[w] = p;
       prefix[w] = acc;
       F::mul(acc, acc, C::denominator(p));
     }
     F::invert(inv, acc);
-    for (u32 w = W - 1; w >= 1; --w) {
+    for (u32 w = W; w-- > 0;) {
       typename F::E zi;
       F::mul(zi, inv, prefix[w]);
       F::mul(inv, inv, C::denominator(pts[w]));
@@ -1019,7 +1023,8 @@ void msm_accumulate_range(stream_t s, const MsmPlan& plan, const typename C::Gen
     const u32 fin = final_level ? 1u : 0u;
     if (first) {
       launch(AccumulateBody<C, true>{nullptr, walk_entries, walk_gens, nullptr, m_ptr, K, fin,
-                                     d_target, out_keys, out_pieces, out_m},
+                                     d_target, out_keys, out_pieces, out_m,
+                                     (walk_gens == gens && opt.gens_normalized) ? 1u : 0u},
              T, s);
       KernelTimer::get().end(s);
       if (tail != s) {
@@ -1028,11 +1033,11 @@ void msm_accumulate_range(stream_t s, const MsmPlan& plan, const typename C::Gen
       }
     } else if (T <= opt.quad_threshold) {
       launch(AccumulateBody<C, false, QuadExec>{lvl_keys, nullptr, nullptr, lvl_pieces, m_ptr, K,
-                                                fin, d_target, out_keys, out_pieces, out_m},
+                                                fin, d_target, out_keys, out_pieces, out_m, 0u},
              T * QuadExec::kLanes, cs);
     } else {
       launch(AccumulateBody<C, false>{lvl_keys, nullptr, nullptr, lvl_pieces, m_ptr, K, fin,
-                                      d_target, out_keys, out_pieces, out_m},
+                                      d_target, out_keys, out_pieces, out_m, 0u},
              T, cs);
     }
     if (final_level)

@@ -179,6 +179,35 @@ extern "C" int emul_check_mul(unsigned field_id, unsigned iters, unsigned seed) 
   }
 }
 
+// binary-Euclid inversion vs the Fermat power (Montgomery fields), incl. 0, 1, 2, p - 1
+template <class F> static int check_invert(unsigned iters, unsigned seed) {
+  unsigned long long st = seed * 0x9E3779B97F4A7C15ull + 3;
+  auto next = [&st]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (u32)(st >> 16); };
+  int bad = 0;
+  for (unsigned it = 0; it < iters; ++it) {
+    typename F::E a, r1, r2, one = F::one(), chk;
+    for (int i = 0; i < F::N; ++i) a.l[i] = next();
+    a.l[F::N - 1] &= 0x0fffffffu;
+    if (it == 0) a = F::zero();
+    if (it == 1) a = F::one();
+    if (it == 2) F::add(a, one, one);
+    if (it == 3) { a = F::modulus(); limbs_sub_small<F::N>(a.l, a.l, 1); }
+    if (it == 4) { a = F::zero(); a.l[0] = 1; }  // plain 1 = R^-1 in the Montgomery domain
+    F::invert(r1, a);
+    F::invert_eea(r2, a);
+    if (!F::equal(r1, r2)) ++bad;
+    if (it) { F::mul(chk, r2, a); if (!F::equal(chk, one)) ++bad; }
+  }
+  return bad;
+}
+extern "C" int emul_check_invert(unsigned field_id, unsigned iters, unsigned seed) {
+  switch (field_id) {
+  case 1: return check_invert<FBls>(iters, seed);
+  case 2: return check_invert<FBn>(iters, seed);
+  default: return check_invert<FGk>(iters, seed);
+  }
+}
+
 // multi-GPU host logic support: partial accumulator points and their combination
 extern "C" unsigned emul_point_bytes(unsigned curve_id) {
   return vt(curve_id).point_bytes;

@@ -14,6 +14,12 @@ def test_production_multiply_schedules_match_reference_schedules(emul):
         assert emul.check_mul(field_id, 4000, seed=field_id + 1) == 0
 
 
+def test_binary_euclid_inversion_matches_fermat(emul):
+    import ctypes as C
+    for field_id in (1, 2, 3):
+        assert int(emul.lib().emul_check_invert(C.c_uint(field_id), C.c_uint(300), C.c_uint(field_id))) == 0
+
+
 def test_golden_commitments(emul):
     assert emul.commit(0, common.golden_columns()).tolist() == common.GOLDEN_COMMITMENTS
 
