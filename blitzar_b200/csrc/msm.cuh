@@ -879,7 +879,7 @@ void msm_accumulate_range(stream_t s, const MsmPlan& plan, const typename C::Gen
     const double mean = (double)max_entries / (double)nkeys;
     if (opt.pair_levels >= 0)
       L = (u32)opt.pair_levels;
-    else if (max_entries >= (1ull << 18))
+    else if (max_entries >= (1ull << 23))  // below ~2^19 terms the per-level fixed costs lose (measured)
       while (L < 6 && (double)(32u << L) <= mean)  // measured on B200: 2 levels at a mean load of 64,
         ++L;                                        // 3 at 128 (tests/pair_timing.py)
     while (L > 0 && max_entries + nkeys * ((1ull << L) - 1) >= (1ull << 32) - (1ull << L))
