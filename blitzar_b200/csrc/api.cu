@@ -1,10 +1,18 @@
 // C-ABI layer: the sxt_* drop-in entry points and the b200_* device-resident extension
-// (include/blitzar_b200.h). Host side is plain C++ over one CUDA stream; all arithmetic runs in
-// the kernels of msm.cuh. There is no CPU fallback: without a usable GPU sxt_init aborts, exactly
-// as the reference's gpu backend does (cbindings/backend.cc:50-64).
+// (include/blitzar_b200.h). Host side is plain C++ over CUDA streams (compute + copy stream per device,
+// an auxiliary stream for the two halves of a batch-affine level); all arithmetic runs in the kernels
+// of msm.cuh / batch_affine.cuh / lanefield.cuh. There is no CPU fallback: without a usable GPU sxt_init
+// aborts, exactly as the reference's gpu backend does (cbindings/backend.cc:50-64).
 //
-// Replaces: cbindings/{backend,pedersen,fixed_pedersen,get_generators,get_one_commit}.cc and the
-// gpu_backend methods they dispatch to (sxt/cbindings/backend/gpu_backend.cc:150-334).
+// Also here: the copy / compute pipeline of host-pointer calls (commit_on), the parallel staging of
+// pageable memory (HostStager), fixed-base handles with their device-built tables (shard_new), and
+// the in-process multi-GPU layer (BLITZAR_B200_DEVICES: worker thread per device; by column, by
+// generator range, sharded handles — commit_host / fixed_host / handle_new).
+//
+// Replaces: cbindings/{backend,pedersen,fixed_pedersen,get_generators,get_one_commit}.cc, the
+// gpu_backend methods they dispatch to (sxt/cbindings/backend/gpu_backend.cc:150-334), the multi-device
+// split of sxt/multiexp/pippenger2/multiexponentiation.h:100-135,248-287 and the handle accessor of
+// sxt/multiexp/pippenger2/in_memory_partition_table_accessor{,_utility}.h.
 #include <algorithm>
 #include <cctype>
 #include <cstdint>

@@ -1,6 +1,7 @@
 // Device-level glue between the C ABI and the MSM engine: descriptor validation, column grouping,
-// generator ingestion and result canonicalisation. Shared by api.cu (product) and the CPU-side
-// emulation harness under tests/emul (test infrastructure).
+// generator ingestion, the choice between a handle's fixed-base table and the variable-base run
+// (prefer_table), result canonicalisation. Shared by api.cu (product) and the CPU-side emulation
+// harness under tests/emul (test infrastructure), both through the per-curve vtables.
 #pragma once
 #include <cstdint>
 #include <vector>

@@ -16,6 +16,12 @@
 // summed by a load-balanced chunk walk (every thread sums exactly K consecutive sorted entries,
 // whatever the bucket-size distribution) followed by a short cascade over chunk-boundary pieces.
 // Bucket arrays live in HBM once per window (no per-block replicas), sized for 180 GB.
+//
+// Round 2: the short Weierstrass curves run the first levels of the bucket sums as batch-affine pair
+// additions (batch_affine.cuh) before the chunk walk; fixed-base calls run in table mode (all windows of
+// a column share one bucket set over a precomputed table 2^(c w) G_i, PrecomputeTableBody /
+// ColumnDesc::table_n — replaces sxt/multiexp/pippenger2/{partition_table,partition_product,
+// combine_reduce}.h); the ed25519 tail kernels are warp-cooperative (lanefield.cuh).
 #pragma once
 #include <algorithm>
 #include <vector>

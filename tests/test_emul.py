@@ -256,3 +256,46 @@ def test_generators_from_reference_partition_table_file(emul, port, curve):
     zero = port.commit(curve, [(np.zeros((0, 4), dtype=np.uint8), 0)] * 2,
                        common.generators_for(port, curve, 1)[0])
     assert common.same(curve, ident, zero)
+
+
+def test_window_major_scatter_option(emul, port):
+    """The (measured-slower, off by default) window-major scatter sorts the same entries."""
+    rng = np.random.default_rng(15)
+    n = 500
+    gens, _ = common.generators_for(port, 0, n)
+    cols = common.random_columns(rng, n, [(0, 32, 0), (-13, 16, 1), (0, 8, 1), (-499, 32, 0), (0, 1, 0)])
+    try:
+        emul.set_scatter_window_major(1)
+        assert common.same(0, emul.commit(0, cols, gens), port.commit(0, cols, gens))
+    finally:
+        emul.set_scatter_window_major(0)
+
+
+@pytest.mark.parametrize("curve", [1, 2, 3])
+def test_batch_affine_pair_levels(emul, port, curve):
+    """Weierstrass accumulation through L batch-affine pair levels (padded buckets, fused passes, the
+    inversion tree with its Euclid top) for several window widths / levels / batch sizes, on generators
+    with duplicates and negations (doublings, cancellations, identity operands inside the pair levels)."""
+    rng = np.random.default_rng(50 + curve)
+    n = 600
+    gens, _ = common.generators_for(port, curve, n)
+    gens[1::7] = gens[0]
+    cols = common.random_columns(rng, n, [(0, 32, 0), (-13, 16, 1), (0, 2, 0)])
+    ones = np.full((n, 1), 3, dtype=np.uint8)
+    sg = np.zeros((n, 1), dtype=np.uint8)
+    sg[::2], sg[1::2] = 1, 0xFF  # +1 / -1 alternating: P + (-P) on the duplicated generators
+    cols += [(ones, 0), (sg, 1)]
+    want = port.commit(curve, cols, gens)
+    try:
+        for c, levels, batch in ((4, 1, 4), (4, 3, 5), (6, 2, 32), (3, 5, 0), (2, 6, 64)):
+            emul.set_tuning(window_bits=c)
+            emul.set_pairs(levels, batch)
+            assert common.same(curve, emul.commit(curve, cols, gens), want), (c, levels, batch)
+        emul.set_ranges(3)  # later ranges: scratch buckets + merge with padded layouts
+        emul.set_tuning(window_bits=4)
+        emul.set_pairs(2, 8)
+        assert common.same(curve, emul.commit(curve, cols, gens), want)
+    finally:
+        emul.set_ranges(1)
+        emul.set_tuning()
+        emul.set_pairs(-1, 0)
