@@ -60,6 +60,8 @@ EngineCtx ctx_of(const State& st) {
     c.tail = st.tail_stream;
   if (const char* env = std::getenv("BLITZAR_B200_GROUP_ENTRIES"))  // test hook: force column groups
     c.opt.max_group_entries = std::strtoull(env, nullptr, 10);
+  if (const char* env = std::getenv("BLITZAR_B200_UNIFORM_ADD"))
+    c.opt.uniform_add = (u32)std::atoi(env);
   if (const char* env = std::getenv("BLITZAR_B200_LANE_TAIL"))
     c.opt.lane_tail = (u32)std::atoi(env);
   if (const char* env = std::getenv("BLITZAR_B200_SCATTER_WM"))

@@ -20,6 +20,8 @@ struct MsmOptions {
                                        // columns are processed as several generator ranges
   int pair_levels = -1;  // batch-affine pair levels (Weierstrass): -1 = from the mean bucket load
   u32 pair_batch = 0;    // pairs per thread of a pair level (0 = 32)
+  u32 uniform_add = 2;  // gathering level: runs start from the identity (no divergent start path);
+                        // 0 off, 1 on, 2 = ed25519 only
   u32 gens_normalized = 0;  // set per call: the generator array is a fixed-base table (Z = 1 entries)
   u32 lane_tail = 1;  // warp-cooperative (lane-sliced) Horner / encoding kernels for ed25519
   u32 scatter_window_major = 0;  // scatter with one thread per (window, term), window-major

@@ -330,7 +330,11 @@ template <class C> struct MergeBucketsBody {
 // strictly inside the chunk are complete and go straight to buckets[key]; the first and last
 // segment may continue in the neighbouring chunks, so they are emitted as pieces (2 per chunk,
 // keys stay sorted) for the next, K/2-times smaller, level. The final level writes everything.
-template <class C, bool kGather, class X = SeqExec> struct AccumulateBody {
+// kUniform (gathering level only): a run starts from the identity and its first generator is ADDED like
+// every other one, so that a run boundary costs the lanes that hit it only a bucket store and a reset
+// instead of a separate generator-to-point conversion path (one more multiplication by a constant) that
+// the rest of the warp waits for; the price is a full addition for the first element of every run.
+template <class C, bool kGather, class X = SeqExec, bool kUniform = false> struct AccumulateBody {
   static constexpr int kBlock = 128;
   // register cap: 168 (3 blocks/SM) for 8-limb fields; 12-limb bls12-381 keeps 255 (2 blocks/SM)
   static constexpr int kMinBlocks = !kGather ? 1 : (C::F::N > 8 ? 2 : 3);
@@ -409,7 +413,23 @@ template <class C, bool kGather, class X = SeqExec> struct AccumulateBody {
         }
         const u32 k = (u32)(ent >> 32);
         const bool negate = ((u32)ent & 1u) != 0;
-        if (i == b) {
+        if (kUniform) {
+          if (i == b) {
+            ga.p = C::identity();
+          } else if (k != cur) {
+            ga.get(acc);
+            if (final_level || !first_seg) {
+              put_bucket(cur, acc, writer);
+            } else if (writer) {
+              out_keys[2 * t] = cur;
+              out_pieces[2 * t] = acc;
+            }
+            first_seg = false;
+            cur = k;
+            ga.p = C::identity();
+          }
+          ga.add(g, negate);
+        } else if (i == b) {
           ga.start(g, negate);
         } else if (k == cur) {
           ga.add(g, negate);
@@ -1028,10 +1048,20 @@ void msm_accumulate_range(stream_t s, const MsmPlan& plan, const typename C::Gen
     }
     const u32 fin = final_level ? 1u : 0u;
     if (first) {
-      launch(AccumulateBody<C, true>{nullptr, walk_entries, walk_gens, nullptr, m_ptr, K, fin,
-                                     d_target, out_keys, out_pieces, out_m,
-                                     (walk_gens == gens && opt.gens_normalized) ? 1u : 0u},
-             T, s);
+      const u32 unit_z = (walk_gens == gens && opt.gens_normalized) ? 1u : 0u;
+      // measured on B200: ed25519 C2 2.894 -> 2.764 ms (a run start is a multiplication by a constant
+      // there); the Weierstrass start is free, so the extra addition loses (bn254 10.71 -> 10.94 ms)
+      const bool uniform =
+          opt.uniform_add == 2 ? C::kCurveId == kRistretto255 : opt.uniform_add != 0;
+      if (uniform)
+        launch(AccumulateBody<C, true, SeqExec, true>{nullptr, walk_entries, walk_gens, nullptr,
+                                                      m_ptr, K, fin, d_target, out_keys, out_pieces,
+                                                      out_m, unit_z},
+               T, s);
+      else
+        launch(AccumulateBody<C, true>{nullptr, walk_entries, walk_gens, nullptr, m_ptr, K, fin,
+                                       d_target, out_keys, out_pieces, out_m, unit_z},
+               T, s);
       KernelTimer::get().end(s);
       if (tail != s) {
         stream_follow(tail, s);

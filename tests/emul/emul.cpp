@@ -59,6 +59,7 @@ void emul_set_builtin(uint64_t np, unsigned window_bits) {
 void emul_set_range_entries(unsigned long long v) { g_opt.max_range_entries = v ? v : (1ull << 31); }
 void emul_set_group_entries(unsigned long long v) { g_opt.max_group_entries = v ? v : (1ull << 30); }
 void emul_set_scatter_window_major(unsigned on) { g_opt.scatter_window_major = on; }
+void emul_set_uniform_add(unsigned on) { g_opt.uniform_add = on; }
 void emul_set_pairs(int levels, unsigned batch) {
   g_opt.pair_levels = levels;
   g_opt.pair_batch = batch;

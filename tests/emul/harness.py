@@ -195,3 +195,7 @@ def generators_from_reference_table(curve_id, path):
 
 def set_scatter_window_major(on=0):
     lib().emul_set_scatter_window_major(C.c_uint(on))
+
+
+def set_uniform_add(on=0):
+    lib().emul_set_uniform_add(C.c_uint(on))
