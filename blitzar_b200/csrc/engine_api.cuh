@@ -1,6 +1,7 @@
 // Type-erased per-curve entry points of the MSM engine. api.cu sees only this header, so the
 // kernels of each curve are compiled exactly once, in that curve's own translation unit.
 #pragma once
+#include <cmath>
 #include <cstdint>
 
 #include "../../include/blitzar_b200.h"
@@ -20,6 +21,7 @@ struct MsmOptions {
                                        // columns are processed as several generator ranges
   int pair_levels = -1;  // batch-affine pair levels (Weierstrass): -1 = from the mean bucket load
   u32 pair_batch = 0;    // pairs per thread of a pair level (0 = 32)
+  int range_skew = 0;   // piece schedule of a multi-range call (range_begin); set by the host layer
   u32 uniform_add = 2;  // gathering level: runs start from the identity (no divergent start path);
                         // 0 off, 1 on, 2 = ed25519 only
   u32 gens_normalized = 0;  // set per call: the generator array is a fixed-base table (Z = 1 entries)
@@ -81,8 +83,21 @@ template <class T> struct DevBuf {
 
 // generator-range r of `num_ranges` over n terms starts here (shared by the engine and the C-ABI
 // layer, which schedules the host-to-device copies of each range)
-inline uint64_t range_begin(uint64_t n, uint32_t r, uint32_t num_ranges) {
-  return n * r / num_ranges;
+// skew > 0: pieces shrink towards the end (upload-bound calls: little work is left after the last
+// byte has arrived); skew < 0: pieces grow (compute-bound calls: the first kernels start early);
+// 0: equal pieces. begin(0) = 0, begin(num_ranges) = n, strictly monotone for n >= num_ranges.
+inline uint64_t range_begin(uint64_t n, uint32_t r, uint32_t num_ranges, int skew = 0) {
+  if (r == 0)
+    return 0;
+  if (r >= num_ranges)
+    return n;
+  if (skew == 0 || n < 64ull * num_ranges)
+    return n * r / num_ranges;
+  const double t = (double)r / (double)num_ranges;
+  const double f = skew > 0 ? 1.0 - (1.0 - t) * std::sqrt(1.0 - t) : t * std::sqrt(t);
+  uint64_t b = (uint64_t)((double)n * f);
+  const uint64_t lo = r, hi = n - (num_ranges - r);  // keep every piece non-empty
+  return b < lo ? lo : (b > hi ? hi : b);
 }
 // called on the host before the engine touches terms [begin, end) (e.g. make the compute stream wait
 // for that range's copies)

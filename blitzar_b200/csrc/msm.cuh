@@ -1212,7 +1212,8 @@ void msm_run(stream_t s, const typename C::Gen* gens, std::vector<ColumnDesc> co
   // several ranges + a second stream: the cascade / merge of range r runs under range r+1
   const bool overlap = num_ranges > 1 && tail != stream_t() && tail != s;
   for (u32 r = 0; r < num_ranges; ++r) {
-    u64 begin = range_begin(plan.max_n, r, num_ranges), end = range_begin(plan.max_n, r + 1, num_ranges);
+    u64 begin = range_begin(plan.max_n, r, num_ranges, opt.range_skew),
+        end = range_begin(plan.max_n, r + 1, num_ranges, opt.range_skew);
     if (hook)
       hook->before_range(begin, end);
     msm_accumulate_range<C>(s, plan, gens, begin, end, r > 0, d_buckets, d_window_used, opt,

@@ -24,7 +24,7 @@ s = torch.empty((n, 32), dtype=torch.uint8).pin_memory()
 s.numpy()[:] = rng.integers(0, 256, (n, 32), dtype=np.uint8)
 s.numpy()[:, 31] &= 0x3F
 ref = None
-for ranges in ("1", "2", "3", "4", "6", "8", None):
+for ranges in (os.environ.get("PIECES", "1,2,3,4,6,8").split(",") + [None]):
     if ranges:
         os.environ["BLITZAR_B200_RANGES"] = ranges
     else:

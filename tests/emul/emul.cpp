@@ -60,6 +60,7 @@ void emul_set_range_entries(unsigned long long v) { g_opt.max_range_entries = v 
 void emul_set_group_entries(unsigned long long v) { g_opt.max_group_entries = v ? v : (1ull << 30); }
 void emul_set_scatter_window_major(unsigned on) { g_opt.scatter_window_major = on; }
 void emul_set_uniform_add(unsigned on) { g_opt.uniform_add = on; }
+void emul_set_range_skew(int skew) { g_opt.range_skew = skew; }
 void emul_set_pairs(int levels, unsigned batch) {
   g_opt.pair_levels = levels;
   g_opt.pair_batch = batch;

@@ -199,3 +199,7 @@ def set_scatter_window_major(on=0):
 
 def set_uniform_add(on=0):
     lib().emul_set_uniform_add(C.c_uint(on))
+
+
+def set_range_skew(skew=0):
+    lib().emul_set_range_skew(C.c_int(skew))
