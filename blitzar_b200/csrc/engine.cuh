@@ -55,8 +55,10 @@ template <class C> struct CurveOps {
       std::vector<ColumnDesc> group(cols.begin() + b, cols.begin() + e);
       const bool whole = b == 0 && e == cols.size();
       // range hooks assume one pass over the generators; several column groups each see all of them
-      if (!whole && hook && b == 0)
+      if (!whole && hook && b == 0) {
         hook->before_range(0, ~0ull);
+        hook->before_accumulate();
+      }
       msm_run<C>(ctx.s, gens, group, out + b, ctx.opt, whole ? num_ranges : 1,
                  whole ? hook : nullptr, ctx.tail);
       b = e;
@@ -72,6 +74,7 @@ template <class C> struct CurveOps {
     bool builtin;  // generate g(offset + i) instead of converting `raw`
     range_wait_fn wait;
     void* wait_user;
+    bool pending = false;  // an ingestion is running on the second stream
     void before_range(u64 begin, u64 end) override {
       if (end > n)
         end = n;
@@ -79,11 +82,22 @@ template <class C> struct CurveOps {
         return;
       if (wait)
         wait(wait_user, begin, end);
-      if (raw)
-        launch(IngestBody<C, false>{raw + begin * C::kAbiGenBytes, gens + begin}, end - begin,
-               ctx->s);
-      else if (builtin)
+      if (raw) {
+        // the sort of this range reads only scalars: the (HBM-bound) ingestion runs beside it on a
+        // second stream and is joined right before the first kernel that gathers generators
+        stream_t aux = aux_stream();
+        stream_follow(aux, ctx->s);
+        launch(IngestBody<C, false>{raw + begin * C::kAbiGenBytes, gens + begin}, end - begin, aux);
+        pending = true;
+      } else if (builtin) {
         launch_builtin(ctx->s, gens + begin, offset_generators + begin, end - begin);
+      }
+    }
+    void before_accumulate() override {
+      if (pending) {
+        stream_follow(ctx->s, aux_stream());
+        pending = false;
+      }
     }
   };
   static void launch_builtin(stream_t s, Gen* gens, uint64_t first, uint64_t count) {
@@ -148,6 +162,7 @@ template <class C> struct CurveOps {
         col.table_n = (u32)ctx.num_builtin;
     }
     run_columns(rctx, gens_ptr, cols, pts, num_ranges ? num_ranges : 1, &hook);
+    hook.before_accumulate();  // (no-op unless a range was ingested without being accumulated)
     if (out_commitments)
       launch_store_commit<C>(s, pts, (unsigned char*)out_commitments, num, ctx.opt.lane_tail != 0);
   }

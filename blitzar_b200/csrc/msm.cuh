@@ -854,6 +854,16 @@ inline MsmPlan msm_make_plan(std::vector<ColumnDesc> cols, const MsmOptions& opt
   return p;
 }
 
+// Optional per-range hook: called before the terms [begin, end) are touched (the C-ABI layer uses
+// it to wait for that range's host-to-device copies and to ingest its generators).
+struct RangeHook {
+  virtual void before_range(u64 begin, u64 end) = 0;
+  // called right before the first kernel that reads the generators of the current range (the sort
+  // does not): lets the hook run generator ingestion on a second stream under the sort
+  virtual void before_accumulate() {}
+  virtual ~RangeHook() {}
+};
+
 // Sort + accumulate the terms [begin, end) of every column into d_buckets (indexed by the plan's
 // keys). gens[i] pairs with term i (absolute index). add_into: buckets already hold the sums of
 // earlier ranges (this range then goes through a scratch bucket array + MergeBucketsBody). Enqueued on
@@ -863,7 +873,8 @@ inline MsmPlan msm_make_plan(std::vector<ColumnDesc> cols, const MsmOptions& opt
 template <class C>
 void msm_accumulate_range(stream_t s, const MsmPlan& plan, const typename C::Gen* gens, u64 begin,
                           u64 end, bool add_into, typename C::Point* d_buckets,
-                          u32* d_window_used, const MsmOptions& opt, stream_t tail) {
+                          u32* d_window_used, const MsmOptions& opt, stream_t tail,
+                          RangeHook* hook = nullptr) {
   typedef typename C::Point Point;
   const u32 ncols = plan.ncols;
   std::vector<ColumnDesc> cols(plan.cols);
@@ -949,6 +960,8 @@ void msm_accumulate_range(stream_t s, const MsmPlan& plan, const typename C::Gen
   const u64* walk_entries = d_entries;
   u64 m_max = max_entries;
   u32* m_ptr = d_m;
+  if (hook)
+    hook->before_accumulate();
   KernelTimer::get().begin(s);
   StageRange nvtx_acc("msm: bucket accumulation");
   if constexpr (C::kBatchAffine) {
@@ -1169,13 +1182,6 @@ void msm_finish(stream_t s, const MsmPlan& plan, const typename C::Point* d_buck
   dev_free(d_cols, s);
 }
 
-// Optional per-range hook: called before the terms [begin, end) are touched (the C-ABI layer uses
-// it to wait for that range's host-to-device copies and to ingest its generators).
-struct RangeHook {
-  virtual void before_range(u64 begin, u64 end) = 0;
-  virtual ~RangeHook() {}
-};
-
 // Computes out[j] = sum_i scalar(j,i) * G_i for every column j. `cols` are host descriptors whose
 // `base` pointers are DEVICE pointers; gens and out are device arrays. The generator range is
 // processed in `num_ranges` contiguous pieces that share one bucket array, so that the sort and
@@ -1217,7 +1223,7 @@ void msm_run(stream_t s, const typename C::Gen* gens, std::vector<ColumnDesc> co
     if (hook)
       hook->before_range(begin, end);
     msm_accumulate_range<C>(s, plan, gens, begin, end, r > 0, d_buckets, d_window_used, opt,
-                            overlap ? tail : s);
+                            overlap ? tail : s, hook);
   }
   if (overlap)
     stream_follow(s, tail);
