@@ -68,3 +68,19 @@ def test_product_sources_never_reference_the_oracle():
                 if pat.search(open(os.path.join(base, f)).read()):
                     bad.append(f)
     assert not bad, bad
+
+
+def test_c_example_compiles_and_links_against_the_library(lib, tmp_path):
+    """examples/cbindings1.c (the reference's example/cbindings1/main.cc in plain C99) compiles against
+    include/blitzar_b200.h and links against the product library: the header is valid C and every
+    entry point it uses resolves. (It is not run here: no GPU, no CPU fallback.)"""
+    _, api = lib
+    exe = str(tmp_path / "cbindings1")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "cbindings1.c"),
+                           "-L", os.path.dirname(api.LIB_PATH), "-lblitzar_b200",
+                           "-Wl,-rpath," + os.path.dirname(api.LIB_PATH), "-o", exe])
+    out = subprocess.check_output(["nm", "-u", exe]).decode()
+    for sym in ("sxt_init", "sxt_curve25519_compute_pedersen_commitments", "sxt_multiexp_handle_new",
+                "sxt_fixed_multiexponentiation"):
+        assert sym in out
